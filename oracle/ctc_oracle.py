@@ -1,0 +1,105 @@
+"""oracle/ctc_oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes front-end of oracle/ctc_oracle.c (the float64 C restatement of
+/root/reference/ctc_fast/ctc-loss/ctc_fast.pyx:13-187) plus a loader for oracle/_ref (the
+reference's own .pyx compiled unmodified by oracle/build_ref.py).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product package (stanford-ctc_b200/) never does.
+"""
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def lib_path():
+    return os.path.join(HERE, "_build", "libctc_oracle.so")
+
+
+def build(force=False):
+    """gcc the C restatement into oracle/_build/ (git-ignored, ships with gpurun)."""
+    src = os.path.join(HERE, "ctc_oracle.c")
+    out = lib_path()
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    if force or not os.path.exists(out) or os.path.getmtime(out) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", src, "-o", out, "-lm"])
+    return out
+
+
+def _lib():
+    global _LIB
+    if _LIB is None:
+        _LIB = ctypes.CDLL(build())
+        _LIB.ctc_oracle_loss.restype = ctypes.c_int
+        _LIB.ctc_oracle_loss.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB.ctc_oracle_best_path.restype = ctypes.c_int
+        _LIB.ctc_oracle_best_path.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_void_p]
+    return _LIB
+
+
+def ctc_loss(params, seq, blank=0):
+    """Same contract as the reference ctc_loss (ctc_fast.pyx:13-14,152): params K x T float64
+    Fortran-contiguous, seq int32; returns (nll, grad K x T float64 F-order, skip)."""
+    if not (isinstance(params, np.ndarray) and params.dtype == np.float64 and params.ndim == 2
+            and params.flags.f_contiguous):
+        raise ValueError("ndarray is not Fortran contiguous")
+    seq = np.ascontiguousarray(seq, dtype=np.int32)
+    K, T = params.shape
+    grad = np.zeros((K, T), dtype=np.float64, order="F")
+    nll = ctypes.c_double(0.0)
+    skip = _lib().ctc_oracle_loss(params.ctypes.data, K, T, seq.ctypes.data, seq.shape[0], int(blank),
+                                  grad.ctypes.data, ctypes.addressof(nll))
+    return nll.value, grad, bool(skip)
+
+
+def decode_best_path(probs, blank=0):
+    probs = np.asfortranarray(probs, dtype=np.float64)
+    K, T = probs.shape
+    hyp = np.zeros(T, dtype=np.int32)
+    align = np.zeros(T, dtype=np.int32)
+    n = _lib().ctc_oracle_best_path(probs.ctypes.data, K, T, int(blank), hyp.ctypes.data, align.ctypes.data)
+    return hyp[:n].tolist(), align[:n].tolist()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref: the unmodified reference extension (kind "reference")
+# ---------------------------------------------------------------------------------------------
+_REF = None
+
+
+def ref_module():
+    """Import the compiled reference ctc_fast from oracle/_ref (None if it was never built)."""
+    global _REF
+    if _REF is None:
+        import importlib.util
+        import sysconfig
+        so = os.path.join(HERE, "_ref", "ctc_fast" + sysconfig.get_config_var("EXT_SUFFIX"))
+        if not os.path.exists(so):
+            return None
+        spec = importlib.util.spec_from_file_location("ctc_fast", so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        _REF = mod
+    return _REF
+
+
+def ref_ctc_loss(params, seq, blank=0):
+    """Call the unmodified reference.  Its failure path does `print e.message`
+    (ctc_fast.pyx:148), which under Python 3 raises AttributeError out of the handler instead of
+    returning skip=True -- map that (and a bare ZeroDivisionError) to skip=True with zero grad."""
+    mod = ref_module()
+    if mod is None:
+        raise RuntimeError("oracle/_ref not built (run oracle/build_ref.py where /root/reference exists)")
+    try:
+        nll, grad, skip = mod.ctc_loss(params, np.ascontiguousarray(seq, dtype=np.int32), blank)
+        return float(nll), grad, bool(skip)
+    except (AttributeError, ZeroDivisionError, FloatingPointError):
+        return float("nan"), np.zeros(params.shape, dtype=np.float64, order="F"), True
