@@ -1,0 +1,135 @@
+/*
+ * ctcb200.h -- C ABI of libctcb200.so, the B200 (sm_100a) compute backend for the
+ * stanford-ctc training hot path (BRNN forward/backward + CTC alpha/beta + Nesterov SGD).
+ *
+ * Every entry point takes plain pointers and sizes (no torch types).  Unless a parameter is
+ * documented as a HOST pointer it is a DEVICE pointer; all work is enqueued asynchronously on
+ * the caller-supplied cudaStream_t (passed as void*).  Return value: 0 on success, a negative
+ * CTCB_E* code otherwise, with a message retrievable from ctcb_last_error().  Numerical
+ * infeasibility of one utterance (the reference's `skip=True`) is NOT an error: it is reported
+ * per utterance in `skip_out`, as /root/reference/ctc_fast/ctc-loss/ctc_fast.pyx:147-149 does.
+ *
+ * The reference interface each entry point replaces is cited as (file:line) relative to
+ * /root/reference/.
+ */
+#ifndef CTCB200_H
+#define CTCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTCB_OK 0
+#define CTCB_EINVAL (-1)   /* bad argument / unsupported shape */
+#define CTCB_ECUDA (-2)    /* CUDA runtime error (see ctcb_last_error) */
+#define CTCB_ENOMEM (-3)   /* caller workspace too small */
+
+/* ---- library ------------------------------------------------------------------------------ */
+int ctcb_version(void);
+const char *ctcb_last_error(void);
+/* Number of kernels this library has launched since it was loaded (bench.py: gpu_launches). */
+uint64_t ctcb_launch_count(void);
+
+/* ---- CTC loss + gradient (replaces ctc_fast.ctc_loss, ctc_fast/ctc-loss/ctc_fast.pyx:13-152;
+ *      call site ctc_fast/nnets/brnnet.py:175, with the softmax of brnnet.py:161-168 fused) ----
+ * acts      : activations of B utterances; element (u, t, k) at acts[u*utt_stride + t*frame_stride + k]
+ *             (strides in elements).  is_prob=0: pre-softmax logits, the softmax is fused;
+ *             is_prob=1: probabilities (the contract of ctc_fast.ctc_loss's `params`).
+ * labels    : concatenated int32 label sequences; utterance u owns labels[label_off[u] .. label_off[u+1])
+ * T_per_utt : int32[B] frame counts (<= Tmax).  Frames t >= T_per_utt[u] get zero gradient.
+ * grad_out  : same indexing as acts; d(nll)/d(logit) = softmax - posterior occupancy
+ *             (ctc_fast.pyx:139-145).  Zero for skipped utterances.
+ * nll_out   : float32[B]  -log p(labels | acts)     (ctc_fast.pyx:152)
+ * skip_out  : int32[B]    1 where a frame normaliser was 0 (ctc_fast.pyx:147-149)
+ * workspace : ctcb_ctc_workspace_bytes(B, Tmax, max_labels) bytes of device scratch
+ */
+size_t ctcb_ctc_workspace_bytes(int B, int Tmax, int max_labels);
+int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t utt_stride, int64_t frame_stride,
+                           const int32_t *labels, const int32_t *label_off, const int32_t *T_per_utt,
+                           int B, int Tmax, int K, int max_labels, int blank,
+                           float *grad_out, float *nll_out, int32_t *skip_out,
+                           void *workspace, size_t ws_bytes, void *stream);
+
+/* ---- best-path decode (replaces ctc_fast.decode_best_path, ctc_fast.pyx:154-187) -----------
+ * hyp_out/align_out: int32[B*Tmax] (row u holds hyp_len_out[u] valid entries).
+ * drop_swbd_noise!=0 reproduces the reference's removal of labels 1, 2 and 8 (ctc_fast.pyx:176-179). */
+int ctcb_ctc_best_path_f32(const float *acts, int64_t utt_stride, int64_t frame_stride,
+                           const int32_t *T_per_utt, int B, int Tmax, int K, int blank,
+                           int drop_swbd_noise, int32_t *hyp_out, int32_t *align_out,
+                           int32_t *hyp_len_out, void *stream);
+
+/* ---- dense fp32 contraction (replaces cudamat cm.dot call sites brnnet.py:140,196,204,227-230) ----
+ * Row-major C[M x N] = alpha * op(A) * op(B) + beta * C, op(X) = X or X^T per transA/transB.
+ * A is M x K (or K x M if transA), leading dimensions in elements.
+ * bias (may be NULL): added per output column n.  relu!=0: C = max(C, 0) after bias.
+ * mask_src (may be NULL, ldc-strided like C): C *= (mask_src > 0).
+ * workspace is used for split-K partial sums (ctcb_gemm_workspace_bytes). */
+size_t ctcb_gemm_workspace_bytes(int M, int N, int K);
+int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha,
+                  const float *A, int64_t lda, const float *B, int64_t ldb, float beta,
+                  float *C, int64_t ldc, const float *bias, int relu, const float *mask_src,
+                  void *workspace, size_t ws_bytes, void *stream);
+
+/* ---- BRNN (replaces nnets.brnnet.NNet, ctc_fast/nnets/brnnet.py:10-277) --------------------- */
+typedef struct ctcb_brnn_config {
+    int32_t inputDim;      /* brnnet.py:10 */
+    int32_t outputDim;
+    int32_t layerSize;
+    int32_t numLayers;
+    int32_t temporalLayer; /* <=0: none.  1..numLayers (numLayers itself is an extension) */
+    int32_t maxT;          /* frames per utterance the buffers are sized for (reference: maxBatch) */
+    int32_t maxB;          /* utterances per step */
+    int32_t maxLabels;     /* longest label sequence */
+    float reg;             /* L2 coefficient (brnnet.py:11,177-183,197-198,244-247) */
+    float maxAct;          /* clip of the temporal layer, 20.0 (brnnet.py:32) */
+} ctcb_brnn_config;
+
+typedef struct ctcb_brnn ctcb_brnn; /* opaque; owns no device memory */
+
+/* Flat parameter vector layout: the reference's `stack` order (brnnet.py:38-41,66-72):
+ * [W1,b1] ... [W_{N+1},b_{N+1}] [Wtf,dummy] [Wtb,dummy]; W row-major (out x in), dummy = 1 float. */
+int64_t ctcb_brnn_param_count(const ctcb_brnn_config *cfg);
+int ctcb_brnn_num_tensors(const ctcb_brnn_config *cfg);                    /* 2 * len(stack) */
+int ctcb_brnn_tensor_info(const ctcb_brnn_config *cfg, int idx, int64_t *offset, int32_t *rows, int32_t *cols);
+size_t ctcb_brnn_workspace_bytes(const ctcb_brnn_config *cfg);
+
+int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out);
+void ctcb_brnn_destroy(ctcb_brnn *h);
+
+/* costAndGrad over a batch (brnnet.py:117-249 per utterance; gradients SUMMED over utterances).
+ * feats     : time-major [Tmax][B][inputDim] fp32 (frame (t,u) contiguous)
+ * params    : flat parameter vector; grads: same layout, overwritten
+ * cost_out  : float32[B] per-utterance nll (L2 term is returned separately in *regcost_out, device float)
+ * probs_out : optional [Tmax][B][outputDim] softmax output (forward-only mode when grads==NULL,
+ *             brnnet.py:171-173)
+ * stats_out : optional device float[4] = {number of non-skipped utterances, sum of their nll,
+ *             number skipped, 0}.  Callers place it directly behind the flat gradient so that the
+ *             data-parallel all-reduce of the gradient carries it along.
+ */
+int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_per_utt,
+                            const int32_t *labels, const int32_t *label_off, int B, int Tmax,
+                            const float *params, float *grads, float *cost_out, int32_t *skip_out,
+                            float *regcost_out, float *probs_out, float *stats_out,
+                            void *workspace, size_t ws_bytes, void *stream);
+
+/* ---- optimiser (replaces sgd.SGD.run arithmetic, ctc_fast/sgd.py:91-161, and
+ *      NNet.updateParams, brnnet.py:251-256) --------------------------------------------------- */
+/* w += scale * u over n floats (updateParams) */
+int ctcb_axpy_f32(float *w, const float *u, float scale, int64_t n, void *stream);
+/* gnorm2_out[0] = sum(g^2) (sgd.py:103-107), deterministic two-stage reduction; scratch >= 4 KB (512 doubles) */
+int ctcb_sumsq_f32(const float *g, int64_t n, float *gnorm2_out, void *scratch, void *stream);
+/* Fused sgd.py:97-100,130-140,161 given w at the look-ahead point w + mom*v:
+ *   w -= mom*v;  alph = alpha*min(1, maxGNorm/sqrt(*gnorm2));  v = mom*v - alph*g;  w += v
+ * gnorm2 is read on the device (no host sync).  n_valid (optional device float): when it reads 0
+ * every utterance of the step was skipped and only the undo `w -= mom*v` is applied, as the
+ * reference's `if skip: continue` does (sgd.py:109-111). */
+int ctcb_sgd_nesterov_step_f32(float *w, float *v, const float *g, int64_t n, float mom, float alpha,
+                               float max_gnorm, const float *gnorm2, const float *n_valid, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTCB200_H */

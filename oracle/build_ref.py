@@ -42,6 +42,7 @@ def build(force=False):
            "-DNPY_NO_DEPRECATED_API=NPY_1_7_API_VERSION",
            "-I", inc_py, "-I", np.get_include(), c_file, "-o", so]
     subprocess.check_call(cmd)
+    os.remove(c_file)  # generated C embeds reference source text: keep only the binary
     return so
 
 

@@ -1,0 +1,354 @@
+// brnn.cu -- batched costAndGrad of the bi-directional recurrent network, orchestrated on one stream.
+//
+// Replaces nnets.brnnet.NNet.costAndGrad (/root/reference/ctc_fast/nnets/brnnet.py:117-249), which
+// runs one utterance at a time as ~8(T-1)+12N+40 cudamat launches with a blocking D2H/H2D round
+// trip through the CPU CTC in the middle.  Here a whole minibatch of utterances is one pass:
+//
+//   layout   : every activation is time-major [T][B][n] fp32 -- one time step of all utterances is a
+//              contiguous (B x n) slab, so the layer contractions are single GEMMs over R = T*B rows
+//              and the recurrences are (B x H)(H x H) products per step.
+//   forward  : per layer one GEMM with bias(+ReLU) fused in the epilogue (brnnet.py:140-141,155-157);
+//              the temporal layer adds the persistent two-direction sweep (sweep.cu) and For+Back.
+//   CTC      : softmax + alpha/beta + gradient in one kernel on the device (ctc.cu); nothing leaves HBM.
+//   backward : per layer dW = delta^T X (split-K GEMM over R), db = column sums, delta <- delta W with
+//              the ReLU mask fused (brnnet.py:196-204,235-237); BPTT sweep; the recurrent weight
+//              gradients are two GEMMs over time-shifted views (brnnet.py:227-230).
+// Gradients of the utterances of the batch are summed (the reference never normalises, cf.
+// ctc/nnet.py:193-195); a skipped utterance contributes nothing.
+#include "common.cuh"
+#include <new>
+
+namespace ctcb {
+int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
+              const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
+              unsigned int *counters, cudaStream_t st);
+int run_add2(const float *x, const float *y, float *z, int64_t n, cudaStream_t st);
+int run_sumsq(const float *g, int64_t n, float *out, float scale, int accumulate, void *scratch, cudaStream_t st);
+
+// ---- small kernels ---------------------------------------------------------------------------
+// column sums of a row-major R x N matrix: stage 1 partials over row blocks, stage 2 final
+constexpr int CS_ROWS = 1024;
+__global__ void colsum_stage1(const float *__restrict__ x, int64_t R, int N, float *__restrict__ partial) {
+    __shared__ float sh[8][33];
+    const int n = blockIdx.x * 32 + threadIdx.x;
+    const int64_t r0 = (int64_t)blockIdx.y * CS_ROWS;
+    const int64_t r1 = (r0 + CS_ROWS < R) ? r0 + CS_ROWS : R;
+    float s = 0.f;
+    if (n < N)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) s += x[r * N + n];
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && n < N) {
+        float t = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t += sh[i][threadIdx.x];
+        partial[(int64_t)blockIdx.y * N + n] = t;
+    }
+}
+__global__ void colsum_stage2(const float *__restrict__ partial, int nblk, int N, float *__restrict__ out) {
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    float s = 0.f;
+    for (int i = 0; i < nblk; ++i) s += partial[(int64_t)i * N + n];
+    out[n] = s;
+}
+
+// row softmax of a row-major R x K matrix (forward-only mode, brnnet.py:161-173); one warp per row
+__global__ void softmax_rows_kernel(const float *__restrict__ x, float *__restrict__ p, int64_t R, int K) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= R) return;
+    const float *xr = x + row * K;
+    float m = -3.4e38f;
+    for (int k = lane; k < K; k += 32) m = fmaxf(m, xr[k]);
+    m = warp_max(m);
+    float z = 0.f;
+    for (int k = lane; k < K; k += 32) z += expf(xr[k] - m);
+    z = warp_sum(z);
+    const float inv = 1.f / z;
+    for (int k = lane; k < K; k += 32) p[row * K + k] = expf(xr[k] - m) * inv;
+}
+
+__global__ void set_scalar_kernel(float *p, float v) { *p = v; }
+
+// stats = {#non-skipped, sum of their nll, #skipped, 0}; one warp
+__global__ void batch_stats_kernel(const float *__restrict__ cost, const int32_t *__restrict__ skip, int B, float *stats) {
+    float nv = 0.f, cs = 0.f, ns = 0.f;
+    for (int u = threadIdx.x; u < B; u += 32) {
+        if (skip[u]) ns += 1.f;
+        else { nv += 1.f; cs += cost[u]; }
+    }
+    nv = warp_sum(nv); cs = warp_sum(cs); ns = warp_sum(ns);
+    if (threadIdx.x == 0) { stats[0] = nv; stats[1] = cs; stats[2] = ns; stats[3] = 0.f; }
+}
+
+}  // namespace ctcb
+
+using namespace ctcb;
+
+struct ctcb_brnn {
+    ctcb_brnn_config cfg;
+    int nlayers;        // N + 1 affine maps
+    int tl;             // temporal layer or 0
+    int sizes[66];      // [D, H.., K]
+};
+
+static int valid_cfg(const ctcb_brnn_config *c) {
+    if (!c) return 0;
+    if (c->inputDim <= 0 || c->outputDim <= 1 || c->layerSize <= 0) return 0;
+    if (c->numLayers < 1 || c->numLayers > 64) return 0;
+    if (c->maxT <= 0 || c->maxB <= 0 || c->maxLabels < 0) return 0;
+    return 1;
+}
+static int eff_tl(const ctcb_brnn_config *c) {
+    return (c->temporalLayer <= 0 || c->temporalLayer > c->numLayers) ? 0 : c->temporalLayer;
+}
+static void layer_sizes(const ctcb_brnn_config *c, int *sizes) {
+    sizes[0] = c->inputDim;
+    for (int i = 1; i <= c->numLayers; ++i) sizes[i] = c->layerSize;
+    sizes[c->numLayers + 1] = c->outputDim;
+}
+
+extern "C" int ctcb_brnn_num_tensors(const ctcb_brnn_config *cfg) {
+    if (!valid_cfg(cfg)) return 0;
+    return 2 * (cfg->numLayers + 1) + (eff_tl(cfg) ? 4 : 0);
+}
+
+extern "C" int ctcb_brnn_tensor_info(const ctcb_brnn_config *cfg, int idx, int64_t *offset, int32_t *rows, int32_t *cols) {
+    if (!valid_cfg(cfg)) return set_error(CTCB_EINVAL, "ctcb_brnn_tensor_info: bad config");
+    const int nt = ctcb_brnn_num_tensors(cfg);
+    if (idx < 0 || idx >= nt) return set_error(CTCB_EINVAL, "ctcb_brnn_tensor_info: index %d out of range", idx);
+    int sizes[66];
+    layer_sizes(cfg, sizes);
+    int64_t off = 0;
+    for (int t = 0; t < nt; ++t) {
+        int r, c;
+        const int nl = cfg->numLayers + 1;
+        if (t < 2 * nl) {
+            const int i = t / 2;
+            if (t % 2 == 0) { r = sizes[i + 1]; c = sizes[i]; }
+            else { r = sizes[i + 1]; c = 1; }
+        } else {
+            if ((t - 2 * nl) % 2 == 0) { r = cfg->layerSize; c = cfg->layerSize; }
+            else { r = 1; c = 1; }   // the reference's `dummy` bias (brnnet.py:60-72)
+        }
+        if (t == idx) {
+            if (offset) *offset = off;
+            if (rows) *rows = r;
+            if (cols) *cols = c;
+            return CTCB_OK;
+        }
+        off += (int64_t)r * c;
+        off = (off + 3) / 4 * 4;   // keep every tensor 16-byte aligned
+    }
+    return CTCB_EINVAL;
+}
+
+extern "C" int64_t ctcb_brnn_param_count(const ctcb_brnn_config *cfg) {
+    const int nt = ctcb_brnn_num_tensors(cfg);
+    if (nt == 0) return 0;
+    int64_t off; int32_t r, c;
+    ctcb_brnn_tensor_info(cfg, nt - 1, &off, &r, &c);
+    return (off + (int64_t)r * c + 3) / 4 * 4;
+}
+
+namespace {
+struct WsLayout {
+    size_t X[66];       // X[1..N] activations, X[N+1] logits
+    size_t For, Back, dFor, dBack, dA, dB;
+    size_t ctc, gemm, colsum, scratch, counters, lens_dummy;
+    size_t total;
+};
+
+WsLayout ws_layout(const ctcb_brnn_config *c) {
+    WsLayout w{};
+    int sizes[66];
+    layer_sizes(c, sizes);
+    const size_t R = (size_t)c->maxT * c->maxB;
+    const int N = c->numLayers, H = c->layerSize, K = c->outputDim;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+    for (int i = 1; i <= N + 1; ++i) w.X[i] = take(R * sizes[i] * sizeof(float));
+    if (eff_tl(c)) {
+        w.For = take(R * H * sizeof(float));
+        w.Back = take(R * H * sizeof(float));
+        w.dFor = take(R * H * sizeof(float));
+        w.dBack = take(R * H * sizeof(float));
+    }
+    const size_t wide = (size_t)(H > K ? H : K);
+    w.dA = take(R * wide * sizeof(float));
+    w.dB = take(R * wide * sizeof(float));
+    w.ctc = take(ctcb_ctc_workspace_bytes(c->maxB, c->maxT, c->maxLabels));
+    size_t g = 0;
+    const int Rint = (int)((R > 0x7fffffff) ? 0x7fffffff : R);
+    for (int i = 0; i <= N; ++i) {
+        size_t b = ctcb_gemm_workspace_bytes(sizes[i + 1], sizes[i], Rint);
+        if (b > g) g = b;
+    }
+    size_t b = ctcb_gemm_workspace_bytes(H, H, Rint);
+    if (b > g) g = b;
+    w.gemm = take(g);
+    w.colsum = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
+    w.scratch = take(8192);
+    w.counters = take(sizeof(unsigned int) * 2 * ((c->maxB + 7) / 8 + 1));
+    w.total = off;
+    return w;
+}
+}  // namespace
+
+extern "C" size_t ctcb_brnn_workspace_bytes(const ctcb_brnn_config *cfg) {
+    if (!valid_cfg(cfg)) return 0;
+    return ws_layout(cfg).total;
+}
+
+extern "C" int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out) {
+    if (!valid_cfg(cfg) || !out) return set_error(CTCB_EINVAL, "ctcb_brnn_create: bad config");
+    ctcb_brnn *h = new (std::nothrow) ctcb_brnn;
+    if (!h) return set_error(CTCB_ENOMEM, "ctcb_brnn_create: out of host memory");
+    h->cfg = *cfg;
+    if (h->cfg.maxAct <= 0.f) h->cfg.maxAct = 20.0f;   // brnnet.py:32
+    h->nlayers = cfg->numLayers + 1;
+    h->tl = eff_tl(cfg);
+    layer_sizes(cfg, h->sizes);
+    *out = h;
+    return CTCB_OK;
+}
+
+extern "C" void ctcb_brnn_destroy(ctcb_brnn *h) { delete h; }
+
+#define TRY(expr)                    \
+    do {                             \
+        int _rc = (expr);            \
+        if (_rc != CTCB_OK) return _rc; \
+    } while (0)
+
+extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_per_utt,
+                                       const int32_t *labels, const int32_t *label_off, int B, int Tmax,
+                                       const float *params, float *grads, float *cost_out, int32_t *skip_out,
+                                       float *regcost_out, float *probs_out, float *stats_out, void *workspace,
+                                       size_t ws_bytes, void *stream) {
+    if (!h || !feats || !T_per_utt || !params)
+        return set_error(CTCB_EINVAL, "ctcb_brnn_cost_and_grad: null pointer argument");
+    const ctcb_brnn_config &c = h->cfg;
+    if (B <= 0 || B > c.maxB || Tmax <= 0 || Tmax > c.maxT)
+        return set_error(CTCB_EINVAL, "ctcb_brnn_cost_and_grad: batch %d x %d frames exceeds the configured %d x %d",
+                         B, Tmax, c.maxB, c.maxT);
+    const bool train = (grads != nullptr);
+    if (train && (!labels || !label_off || !cost_out || !skip_out))
+        return set_error(CTCB_EINVAL, "ctcb_brnn_cost_and_grad: training mode needs labels and cost/skip outputs");
+    if (!train && !probs_out)
+        return set_error(CTCB_EINVAL, "ctcb_brnn_cost_and_grad: forward-only mode needs probs_out");
+    const WsLayout w = ws_layout(&c);
+    if (!workspace || ws_bytes < w.total)
+        return set_error(CTCB_ENOMEM, "ctcb_brnn_cost_and_grad: workspace %zu < %zu bytes", ws_bytes, w.total);
+    cudaStream_t st = (cudaStream_t)stream;
+    char *ws = (char *)workspace;
+    const int N = c.numLayers, H = c.layerSize, K = c.outputDim, tl = h->tl;
+    const int *sz = h->sizes;
+    const int64_t R = (int64_t)Tmax * B;
+    if (R > 0x7fffffff) return set_error(CTCB_EINVAL, "ctcb_brnn_cost_and_grad: T*B too large");
+    auto Xbuf = [&](int i) -> float * { return (float *)(ws + w.X[i]); };
+    auto P = [&](int idx) -> const float * {
+        int64_t off; ctcb_brnn_tensor_info(&c, idx, &off, nullptr, nullptr); return params + off;
+    };
+    auto G = [&](int idx) -> float * {
+        int64_t off; ctcb_brnn_tensor_info(&c, idx, &off, nullptr, nullptr); return grads + off;
+    };
+    float *For = (float *)(ws + w.For), *Back = (float *)(ws + w.Back);
+    float *dFor = (float *)(ws + w.dFor), *dBack = (float *)(ws + w.dBack);
+    void *gws = ws + w.gemm;
+    const size_t gws_bytes = w.colsum - w.gemm;
+    unsigned int *counters = (unsigned int *)(ws + w.counters);
+    const int iWtf = 2 * (N + 1), iWtb = 2 * (N + 1) + 2;
+
+    // ---------------------------------------------------------------- forward (brnnet.py:136-157)
+    for (int i = 1; i <= N + 1; ++i) {
+        const float *in = (i == 1) ? feats : Xbuf(i - 1);
+        const int relu = (i <= N && i != tl) ? 1 : 0;
+        TRY(ctcb_gemm_f32(0, 1, (int)R, sz[i], sz[i - 1], 1.f, in, sz[i - 1], P(2 * (i - 1)), sz[i - 1], 0.f,
+                          Xbuf(i), sz[i], P(2 * (i - 1) + 1), relu, nullptr, gws, gws_bytes, st));
+        if (i == tl) {
+            TRY(run_sweep(0, Tmax, B, H, T_per_utt, Xbuf(i), P(iWtf), P(iWtb), For, Back, nullptr, nullptr,
+                          c.maxAct, counters, st));
+            TRY(run_add2(For, Back, Xbuf(i), R * H, st));     // brnnet.py:153
+        }
+    }
+    float *logits = Xbuf(N + 1);
+    if (probs_out) {
+        const int wpb = 8;
+        softmax_rows_kernel<<<(unsigned)((R + wpb - 1) / wpb), wpb * 32, 0, st>>>(logits, probs_out, R, K);
+        CTCB_LAUNCH_CHECK();
+    }
+    if (!train) return CTCB_OK;
+
+    // ---------------------------------------------------------------- CTC (brnnet.py:161-175)
+    float *dcur = (float *)(ws + w.dA), *doth = (float *)(ws + w.dB);
+    TRY(ctcb_ctc_loss_grad_f32(logits, 0, (int64_t)K, (int64_t)B * K, labels, label_off, T_per_utt, B, Tmax, K,
+                               c.maxLabels, 0, dcur, cost_out, skip_out, ws + w.ctc, w.gemm - w.ctc, st));
+
+    if (stats_out) {
+        batch_stats_kernel<<<1, 32, 0, st>>>(cost_out, skip_out, B, stats_out);
+        CTCB_LAUNCH_CHECK();
+    }
+
+    // ---------------------------------------------------------------- backward (brnnet.py:188-243)
+    for (int i = N; i >= 0; --i) {
+        const float *Xi = (i == 0) ? feats : Xbuf(i);
+        const int n_out = sz[i + 1], n_in = sz[i];
+        // dW = delta^T . X_i   (brnnet.py:196)
+        TRY(ctcb_gemm_f32(1, 0, n_out, n_in, (int)R, 1.f, dcur, n_out, Xi, n_in, 0.f, G(2 * i), n_in, nullptr, 0,
+                          nullptr, gws, gws_bytes, st));
+        // db = row sums of delta   (brnnet.py:200)
+        {
+            const int nblk = (int)((R + CS_ROWS - 1) / CS_ROWS);
+            float *part = (float *)(ws + w.colsum);
+            colsum_stage1<<<dim3((n_out + 31) / 32, nblk), dim3(32, 8), 0, st>>>(dcur, R, n_out, part);
+            CTCB_LAUNCH_CHECK();
+            colsum_stage2<<<(n_out + 127) / 128, 128, 0, st>>>(part, nblk, n_out, G(2 * i + 1));
+            CTCB_LAUNCH_CHECK();
+        }
+        if (i > 0) {
+            // delta <- delta . W, with the ReLU mask sign(hActs[i]) fused (brnnet.py:203-204,235-237)
+            const float *mask = (i != tl) ? Xi : nullptr;
+            TRY(ctcb_gemm_f32(0, 0, (int)R, n_in, n_out, 1.f, dcur, n_out, P(2 * i), n_in, 0.f, doth, n_in,
+                              nullptr, 0, mask, gws, gws_bytes, st));
+            if (i == tl) {   // brnnet.py:207-233
+                TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), P(iWtb), dFor, dBack, For, Back, c.maxAct,
+                              counters, st));
+                if (Tmax > 1) {
+                    const int64_t Rm = R - B;
+                    TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dFor + (int64_t)B * H, H, For, H, 0.f, G(iWtf), H,
+                                      nullptr, 0, nullptr, gws, gws_bytes, st));
+                    TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dBack, H, Back + (int64_t)B * H, H, 0.f, G(iWtb), H,
+                                      nullptr, 0, nullptr, gws, gws_bytes, st));
+                } else {
+                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf), 0, sizeof(float) * H * H, st));
+                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb), 0, sizeof(float) * H * H, st));
+                }
+                TRY(run_add2(dFor, dBack, doth, R * H, st));
+            }
+            float *t = dcur; dcur = doth; doth = t;
+        }
+    }
+    if (tl) {   // the `dummy` biases never receive gradient
+        CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf + 1), 0, sizeof(float), st));
+        CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb + 1), 0, sizeof(float), st));
+    }
+
+    // ---------------------------------------------------------------- L2 (brnnet.py:177-183,197-198,244-247)
+    if (regcost_out) {
+        set_scalar_kernel<<<1, 1, 0, st>>>(regcost_out, 0.f);
+        CTCB_LAUNCH_CHECK();
+    }
+    if (c.reg > 0.f) {
+        const int nt = ctcb_brnn_num_tensors(&c);
+        for (int idx = 0; idx < nt; idx += 2) {
+            int64_t off; int32_t r, cc;
+            ctcb_brnn_tensor_info(&c, idx, &off, &r, &cc);
+            const int64_t n = (int64_t)r * cc;
+            TRY(ctcb_axpy_f32(grads + off, params + off, c.reg, n, st));
+            if (regcost_out) TRY(run_sumsq(params + off, n, regcost_out, 0.5f * c.reg, 1, ws + w.scratch, st));
+        }
+    }
+    return CTCB_OK;
+}

@@ -1,0 +1,179 @@
+"""sgd -- drop-in for /root/reference/ctc_fast/sgd.py (class SGD), computed by libctcb200.
+
+Same constructor, attributes and methods as the reference (sgd.py:10-11, :36, :44, :57):
+
+    SGD(model, maxBatch, alpha=1e-2, optimizer='nesterov', momentum=0.9, maxGradNorm=1500)
+    run(data_dict, alis, keys, sizes); toFile(fid); fromFile(fid)
+    attributes: alpha, it, costt, expcost, regcost, velocity, momentum, maxGNorm
+
+New, additive: `batchSize` utterances per optimisation step (1 reproduces the reference's
+per-utterance schedule exactly) and data parallelism -- when torch.distributed is initialised the
+`batchSize` utterances of a step are sharded over the ranks and the flat gradient is summed with ONE
+all-reduce (NCCL over NVLink) before the identical, redundant update on every rank.  The clip
+threshold `maxGradNorm` applies to the norm of the summed (reduced) gradient.
+"""
+import logging
+import pickle
+import random
+
+import numpy as np
+
+import _ctcb
+from _ctcb import lib, check, ptr
+from nnets.brnnet import FlatList
+
+
+class SGD:
+
+    def __init__(self, model, maxBatch, alpha=1e-2, optimizer='nesterov',
+                 momentum=0.9, maxGradNorm=1500, batchSize=1, verbose=True):
+        torch = _ctcb.require_cuda()
+        self._torch = torch
+        self.model = model
+        self.maxBatch = maxBatch
+        self.it = 0
+        self.momentum = momentum  # momentum
+        self.alpha = alpha  # learning rate
+        self.optimizer = optimizer
+        self.maxGNorm = maxGradNorm  # gradient clip norm value
+        self.batchSize = batchSize
+        self.verbose = verbose
+        # the reference's adagrad branch is dead code (`assert False`, sgd.py:24-26)
+        assert self.optimizer == 'nesterov', "only the nesterov optimizer exists (sgd.py:24-26)"
+
+        self._vflat = torch.zeros(model.nparams, dtype=torch.float32, device=model.dev)
+        self.velocity = FlatList(model._views(self._vflat), self._vflat)
+        self._gnorm2 = torch.zeros(1, dtype=torch.float32, device=model.dev)
+        self._scratch = torch.zeros(8192, dtype=torch.uint8, device=model.dev)
+
+        self.costt = []
+        self.expcost = []
+        self.regcost = []
+
+    # ------------------------------------------------------------------ distributed plumbing
+    def _world(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist, dist.get_rank(), dist.get_world_size()
+        return None, 0, 1
+
+    # ------------------------------------------------------------------ persistence (sgd.py:36-55)
+    def toFile(self, fid):
+        stack = [[w.cpu().numpy(), b.cpu().numpy()] for w, b in self.velocity]
+        pickle.dump([self.it, self.costt, self.expcost, stack], fid)
+
+    def fromFile(self, fid):
+        torch = self._torch
+        try:
+            params = pickle.load(fid)
+        except UnicodeDecodeError:
+            fid.seek(0)
+            params = pickle.load(fid, encoding="latin1")
+        it, costt, expcost, stack = params
+        self.it = it
+        self.costt = costt
+        self.expcost = expcost
+        for (w, b), (wi, bi) in zip(self.velocity, stack):
+            w.copy_(torch.from_numpy(np.ascontiguousarray(wi, dtype=np.float32).reshape(tuple(w.shape))))
+            b.copy_(torch.from_numpy(np.ascontiguousarray(bi, dtype=np.float32).reshape(tuple(b.shape))))
+
+    # ------------------------------------------------------------------ one optimisation step
+    def step_device(self, batch, mom):
+        """Enqueue one full Nesterov step for a staged DeviceBatch; never synchronises with the host.
+        sgd.py:91-161: look-ahead, costAndGrad, (all-reduce), global norm, clip, velocity, update."""
+        m = self.model
+        stream = _ctcb.current_stream()
+        # w = w + mom*velocity (evaluate gradient at future point)      sgd.py:91-93
+        check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, stream))
+        m.costAndGradDevice(batch)
+        dist, rank, world = self._world()
+        if world > 1:
+            dist.all_reduce(m.grads_ext)                               # sum over ranks, NCCL
+        # gnorm over all parameters as one vector                       sgd.py:103-107
+        check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch), stream))
+        # undo look-ahead, clip, velocity, update                       sgd.py:97-100,130-140,161
+        check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams, float(mom),
+                                             float(self.alpha), float(self.maxGNorm), ptr(self._gnorm2),
+                                             ptr(m.stats), stream))
+
+    def _momentum_now(self):
+        return 0.5 if self.it <= 10 else self.momentum                  # sgd.py:64-74
+
+    def run(self, data_dict, alis, keys, sizes):
+        """Runs stochastic gradient descent with nesterov acceleration.  Model is objective."""
+        torch = self._torch
+        m = self.model
+        dist, rank, world = self._world()
+
+        # randomly select minibatch
+        random.shuffle(keys)
+
+        step = max(1, self.batchSize)
+        for k0 in range(0, len(keys), step):
+            chunk = keys[k0:k0 + step]
+            self.it += 1
+            mom = self._momentum_now()
+
+            datas, labels, used = [], [], []
+            for k in chunk:
+                mb_data = data_dict[k]
+                if mb_data.shape[1] > self.maxBatch:
+                    logging.info("SKIPPING utt exceeds batch length (Utterance length %d)." % mb_data.shape[1])
+                    continue
+                mb_labels = np.array(alis[k], dtype=np.int32)
+                if mb_data.shape[1] < mb_labels.shape[0]:
+                    logging.info("SKIPPING utt frames less than label length "
+                                 "(Utterance length %d, Num Labels %d)." % (mb_data.shape[1], mb_labels.shape[0]))
+                    continue
+                datas.append(mb_data)
+                labels.append(mb_labels)
+                used.append(k)
+            if world > 1:          # shard the step's utterances over the ranks
+                datas, labels, used = datas[rank::world], labels[rank::world], used[rank::world]
+            if world == 1 and not datas:
+                continue
+
+            if datas:
+                m._batch.pack(datas, labels).upload()
+            else:                  # this rank has no utterance this step: contribute zeros
+                m._batch.B = 0
+            if m._batch.B > 0:
+                self.step_device(m._batch, mom)
+            else:
+                m.grads_ext.zero_()
+                dist.all_reduce(m.grads_ext)
+                check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch),
+                                         _ctcb.current_stream()))
+                check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, _ctcb.current_stream()))
+                check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams,
+                                                     float(mom), float(self.alpha), float(self.maxGNorm),
+                                                     ptr(self._gnorm2), ptr(m.stats), _ctcb.current_stream()))
+
+            # one small D2H per step for the log line, as the reference prints every iteration
+            host = torch.cat([m.stats, self._gnorm2, m._regcost]).cpu().numpy()
+            nvalid, costsum, nskip = float(host[0]), float(host[1]), float(host[2])
+            gnorm = float(np.sqrt(host[4]))
+            m.regcost = float(host[5])
+            if nvalid == 0:
+                logging.info("SKIPPING: Keys=%s" % (",".join(str(k) for k in used)))
+                continue
+            cost = costsum / nvalid + (m.regcost if m.reg > 0 else 0.0)
+
+            if np.isfinite(cost):
+                # compute exponentially weighted cost                   sgd.py:113-119
+                if len(self.expcost) > 0:
+                    self.expcost.append(.01 * cost + .99 * self.expcost[-1])
+                else:
+                    self.expcost.append(cost)
+                self.costt.append(cost)
+                if m.reg > 0.0:
+                    rc = m.regcost
+                    if len(self.regcost) > 0:
+                        self.regcost.append(0.01 * rc + 0.99 * self.regcost[-1])
+                    else:
+                        self.regcost.append(rc)
+
+            if self.verbose and rank == 0 and self.it % 1 == 0:
+                print("Iter %d : Cost=%.4f, ExpCost=%.4f, GradNorm=%.4f, SeqLen=%d, NumFrames=%d."
+                      % (self.it, cost, self.expcost[-1] if self.expcost else float('nan'), gnorm,
+                         sum(l.shape[0] for l in labels), sum(d.shape[1] for d in datas)))
