@@ -32,6 +32,12 @@ int ctcb_version(void);
 const char *ctcb_last_error(void);
 /* Number of kernels this library has launched since it was loaded (bench.py: gpu_launches). */
 uint64_t ctcb_launch_count(void);
+/* Per-phase device timing with CUDA events on the launching stream (bench.py roofline). When enabled,
+ * every phase of ctcb_brnn_cost_and_grad and the optimiser entry points is bracketed by events;
+ * ctcb_profile_report synchronises the device and writes a JSON object
+ * {"phase": {"count": n, "total_ms": t}, ...} into buf, then clears the records. */
+void ctcb_profile_enable(int on);
+int ctcb_profile_report(char *buf, size_t cap);
 
 /* ---- CTC loss + gradient (replaces ctc_fast.ctc_loss, ctc_fast/ctc-loss/ctc_fast.pyx:13-152;
  *      call site ctc_fast/nnets/brnnet.py:175, with the softmax of brnnet.py:161-168 fused) ----

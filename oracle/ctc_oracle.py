@@ -84,9 +84,16 @@ def ref_module():
         so = os.path.join(HERE, "_ref", "ctc_fast" + sysconfig.get_config_var("EXT_SUFFIX"))
         if not os.path.exists(so):
             return None
+        # The extension's init symbol is PyInit_ctc_fast, so it must be loaded under that name; keep it
+        # OUT of sys.modules so that `import ctc_fast` still resolves to the product's drop-in module.
+        prev = sys.modules.get("ctc_fast")
         spec = importlib.util.spec_from_file_location("ctc_fast", so)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
+        if prev is not None:
+            sys.modules["ctc_fast"] = prev
+        else:
+            sys.modules.pop("ctc_fast", None)
         _REF = mod
     return _REF
 

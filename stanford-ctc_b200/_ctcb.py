@@ -31,6 +31,8 @@ _PROTOS = {
     "ctcb_version": (c_int, []),
     "ctcb_last_error": (ctypes.c_char_p, []),
     "ctcb_launch_count": (ctypes.c_uint64, []),
+    "ctcb_profile_enable": (None, [c_int]),
+    "ctcb_profile_report": (c_int, [ctypes.c_char_p, c_sz]),
     "ctcb_ctc_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "ctcb_ctc_loss_grad_f32": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int,
                                        c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

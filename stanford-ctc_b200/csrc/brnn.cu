@@ -265,11 +265,18 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     for (int i = 1; i <= N + 1; ++i) {
         const float *in = (i == 1) ? feats : Xbuf(i - 1);
         const int relu = (i <= N && i != tl) ? 1 : 0;
+        {
+        ProfScope ps("gemm_fwd", st);
         TRY(ctcb_gemm_f32(0, 1, (int)R, sz[i], sz[i - 1], 1.f, in, sz[i - 1], P(2 * (i - 1)), sz[i - 1], 0.f,
                           Xbuf(i), sz[i], P(2 * (i - 1) + 1), relu, nullptr, gws, gws_bytes, st));
+        }
         if (i == tl) {
+            {
+            ProfScope ps("sweep_fwd", st);
             TRY(run_sweep(0, Tmax, B, H, T_per_utt, Xbuf(i), P(iWtf), P(iWtb), For, Back, nullptr, nullptr,
                           c.maxAct, counters, st));
+            }
+            ProfScope ps("elementwise", st);
             TRY(run_add2(For, Back, Xbuf(i), R * H, st));     // brnnet.py:153
         }
     }
@@ -283,8 +290,11 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
 
     // ---------------------------------------------------------------- CTC (brnnet.py:161-175)
     float *dcur = (float *)(ws + w.dA), *doth = (float *)(ws + w.dB);
+    {
+    ProfScope ps("ctc", st);
     TRY(ctcb_ctc_loss_grad_f32(logits, 0, (int64_t)K, (int64_t)B * K, labels, label_off, T_per_utt, B, Tmax, K,
                                c.maxLabels, 0, dcur, cost_out, skip_out, ws + w.ctc, w.gemm - w.ctc, st));
+    }
 
     if (stats_out) {
         batch_stats_kernel<<<1, 32, 0, st>>>(cost_out, skip_out, B, stats_out);
@@ -296,10 +306,14 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
         const float *Xi = (i == 0) ? feats : Xbuf(i);
         const int n_out = sz[i + 1], n_in = sz[i];
         // dW = delta^T . X_i   (brnnet.py:196)
+        {
+        ProfScope ps("gemm_dw", st);
         TRY(ctcb_gemm_f32(1, 0, n_out, n_in, (int)R, 1.f, dcur, n_out, Xi, n_in, 0.f, G(2 * i), n_in, nullptr, 0,
                           nullptr, gws, gws_bytes, st));
+        }
         // db = row sums of delta   (brnnet.py:200)
         {
+            ProfScope ps("colsum", st);
             const int nblk = (int)((R + CS_ROWS - 1) / CS_ROWS);
             float *part = (float *)(ws + w.colsum);
             colsum_stage1<<<dim3((n_out + 31) / 32, nblk), dim3(32, 8), 0, st>>>(dcur, R, n_out, part);
@@ -310,11 +324,18 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
         if (i > 0) {
             // delta <- delta . W, with the ReLU mask sign(hActs[i]) fused (brnnet.py:203-204,235-237)
             const float *mask = (i != tl) ? Xi : nullptr;
+            {
+            ProfScope ps("gemm_delta", st);
             TRY(ctcb_gemm_f32(0, 0, (int)R, n_in, n_out, 1.f, dcur, n_out, P(2 * i), n_in, 0.f, doth, n_in,
                               nullptr, 0, mask, gws, gws_bytes, st));
+            }
             if (i == tl) {   // brnnet.py:207-233
+                {
+                ProfScope ps("sweep_bptt", st);
                 TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), P(iWtb), dFor, dBack, For, Back, c.maxAct,
                               counters, st));
+                }
+                ProfScope ps("gemm_dw_rec", st);
                 if (Tmax > 1) {
                     const int64_t Rm = R - B;
                     TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dFor + (int64_t)B * H, H, For, H, 0.f, G(iWtf), H,

@@ -1,6 +1,10 @@
 // common.cu -- error string, launch counter, device queries.
 #include "common.cuh"
 #include <stdarg.h>
+#include <string.h>
+#include <map>
+#include <string>
+#include <vector>
 
 namespace ctcb {
 thread_local char g_last_error[512] = "";
@@ -23,7 +27,57 @@ int num_sms() {
     }
     return n;
 }
+
+static bool g_prof_on = false;
+struct ProfRec { std::string name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+ProfScope::ProfScope(const char *name, cudaStream_t s) : idx(-1), st(s) {
+    if (!g_prof_on) return;
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, s);
+    g_prof.push_back(r);
+    idx = (int)g_prof.size() - 1;
+}
+ProfScope::~ProfScope() {
+    if (idx >= 0) cudaEventRecord(g_prof[idx].b, st);
+}
 }  // namespace ctcb
+
+extern "C" void ctcb_profile_enable(int on) { ctcb::g_prof_on = (on != 0); }
+
+extern "C" int ctcb_profile_report(char *buf, size_t cap) {
+    using namespace ctcb;
+    if (!buf || cap == 0) return set_error(CTCB_EINVAL, "ctcb_profile_report: no buffer");
+    if (cudaDeviceSynchronize() != cudaSuccess) return set_error(CTCB_ECUDA, "ctcb_profile_report: sync failed");
+    std::map<std::string, std::pair<int, double>> agg;
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            auto &e = agg[r.name];
+            e.first += 1;
+            e.second += ms;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    g_prof.clear();
+    std::string out = "{";
+    bool first = true;
+    for (auto &kv : agg) {
+        char tmp[256];
+        snprintf(tmp, sizeof(tmp), "%s\"%s\": {\"count\": %d, \"total_ms\": %.6f}", first ? "" : ", ",
+                 kv.first.c_str(), kv.second.first, kv.second.second);
+        out += tmp;
+        first = false;
+    }
+    out += "}";
+    if (out.size() + 1 > cap) return set_error(CTCB_ENOMEM, "ctcb_profile_report: buffer too small");
+    memcpy(buf, out.c_str(), out.size() + 1);
+    return CTCB_OK;
+}
 
 extern "C" int ctcb_version(void) { return 100; }
 extern "C" const char *ctcb_last_error(void) { return ctcb::g_last_error; }

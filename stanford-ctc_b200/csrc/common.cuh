@@ -34,6 +34,15 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add((uint64_t)n, std:
 
 int num_sms();
 
+// Optional per-phase device timing (ctcb_profile_*): CUDA events recorded on the launching stream
+// around each phase of the step; off by default so the timed benchmark region carries no events.
+struct ProfScope {
+    int idx;
+    cudaStream_t st;
+    ProfScope(const char *name, cudaStream_t s);
+    ~ProfScope();
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -96,6 +96,7 @@ using namespace ctcb;
 extern "C" int ctcb_axpy_f32(float *w, const float *u, float scale, int64_t n, void *stream) {
     if (n <= 0) return CTCB_OK;
     if (!w || !u) return set_error(CTCB_EINVAL, "ctcb_axpy_f32: null pointer");
+    ProfScope ps("sgd", (cudaStream_t)stream);
     axpy_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(w, u, scale, n);
     CTCB_LAUNCH_CHECK();
     return CTCB_OK;
@@ -103,6 +104,7 @@ extern "C" int ctcb_axpy_f32(float *w, const float *u, float scale, int64_t n, v
 
 extern "C" int ctcb_sumsq_f32(const float *g, int64_t n, float *gnorm2_out, void *scratch, void *stream) {
     if (!g || !gnorm2_out || !scratch) return set_error(CTCB_EINVAL, "ctcb_sumsq_f32: null pointer");
+    ProfScope ps("sgd", (cudaStream_t)stream);
     return run_sumsq(g, n, gnorm2_out, 1.0f, 0, scratch, (cudaStream_t)stream);
 }
 
@@ -110,6 +112,7 @@ extern "C" int ctcb_sgd_nesterov_step_f32(float *w, float *v, const float *g, in
                                           float max_gnorm, const float *gnorm2, const float *n_valid, void *stream) {
     if (n <= 0) return CTCB_OK;
     if (!w || !v || !g || !gnorm2) return set_error(CTCB_EINVAL, "ctcb_sgd_nesterov_step_f32: null pointer");
+    ProfScope ps("sgd", (cudaStream_t)stream);
     nesterov_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(w, v, g, n, mom, alpha, max_gnorm, gnorm2, n_valid);
     CTCB_LAUNCH_CHECK();
     return CTCB_OK;

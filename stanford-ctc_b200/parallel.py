@@ -1,0 +1,38 @@
+"""parallel -- host-side logic of the data-parallel step (pure Python, no CUDA).
+
+The reference has no multi-GPU training (one process, one GPU, one utterance per step:
+/root/reference/ctc_fast/runNNet.py:117-120, sgd.py:70-95).  Utterances are independent until the
+parameter update, so a step's minibatch is sharded over ranks and the flat gradient (with its
+4-float statistics tail) is summed by ONE all-reduce; every rank then applies the identical update.
+"""
+
+
+def shard(items, rank, world):
+    """Round-robin shard of one step's utterances: rank r takes items r, r+world, ...  Every item is
+    owned by exactly one rank and the per-rank counts differ by at most one."""
+    if world <= 1:
+        return list(items)
+    return list(items[rank::world])
+
+
+def per_rank_capacity(batch_size, world):
+    """Utterance capacity each rank must allocate for a global step of batch_size utterances."""
+    return (batch_size + world - 1) // max(world, 1)
+
+
+def world_info():
+    """(dist module or None, rank, world) from torch.distributed if it is initialised."""
+    try:
+        import torch.distributed as dist
+    except Exception:
+        return None, 0, 1
+    if dist.is_available() and dist.is_initialized():
+        return dist, dist.get_rank(), dist.get_world_size()
+    return None, 0, 1
+
+
+def allreduce_sum(dist, flat):
+    """Sum the flat gradient (+ statistics tail) over ranks, in place."""
+    if dist is not None:
+        dist.all_reduce(flat)
+    return flat

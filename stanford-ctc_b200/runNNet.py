@@ -19,6 +19,7 @@ from os.path import join as pjoin
 import numpy as np
 
 import dataLoader as dl
+import parallel
 import nnets.brnnet as rnnet
 import sgd
 from run_utils import dump_config, load_config, CfgStruct, get_git_revision, get_hostname, TimeString, touch_file
@@ -146,7 +147,7 @@ def run(args=None):
     alisDir = opts.alisDir if opts.alisDir else opts.dataDir
     loader = dl.DataLoader(opts.dataDir, opts.rawDim, opts.inputDim, alisDir)
 
-    per_rank = (opts.batchSize + world - 1) // world
+    per_rank = parallel.per_rank_capacity(opts.batchSize, world)
     nn = rnnet.NNet(opts.inputDim, opts.outputDim, opts.layerSize, opts.numLayers, opts.maxUttLen,
                     temporalLayer=opts.temporalLayer, reg=opts.reg, maxUtts=per_rank,
                     maxLabels=min(opts.maxLabels, opts.maxUttLen))

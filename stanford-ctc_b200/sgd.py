@@ -21,6 +21,7 @@ import numpy as np
 import _ctcb
 from _ctcb import lib, check, ptr
 from nnets.brnnet import FlatList
+import parallel
 
 
 class SGD:
@@ -52,10 +53,7 @@ class SGD:
 
     # ------------------------------------------------------------------ distributed plumbing
     def _world(self):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            return dist, dist.get_rank(), dist.get_world_size()
-        return None, 0, 1
+        return parallel.world_info()
 
     # ------------------------------------------------------------------ persistence (sgd.py:36-55)
     def toFile(self, fid):
@@ -88,7 +86,7 @@ class SGD:
         m.costAndGradDevice(batch)
         dist, rank, world = self._world()
         if world > 1:
-            dist.all_reduce(m.grads_ext)                               # sum over ranks, NCCL
+            parallel.allreduce_sum(dist, m.grads_ext)                  # sum over ranks, NCCL
         # gnorm over all parameters as one vector                       sgd.py:103-107
         check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch), stream))
         # undo look-ahead, clip, velocity, update                       sgd.py:97-100,130-140,161
@@ -129,7 +127,7 @@ class SGD:
                 labels.append(mb_labels)
                 used.append(k)
             if world > 1:          # shard the step's utterances over the ranks
-                datas, labels, used = datas[rank::world], labels[rank::world], used[rank::world]
+                datas, labels, used = (parallel.shard(x, rank, world) for x in (datas, labels, used))
             if world == 1 and not datas:
                 continue
 
@@ -141,7 +139,7 @@ class SGD:
                 self.step_device(m._batch, mom)
             else:
                 m.grads_ext.zero_()
-                dist.all_reduce(m.grads_ext)
+                parallel.allreduce_sum(dist, m.grads_ext)
                 check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch),
                                          _ctcb.current_stream()))
                 check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, _ctcb.current_stream()))

@@ -1,0 +1,114 @@
+"""CPU tests of the host-side mirror of the reference interface: data files, run utilities, likelihood
+writer format, step sharding -- including a world_size-2 gloo run of the data-parallel reduction."""
+import os
+import struct
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_dataloader_roundtrip(tmp_path):
+    import dataLoader as dl
+    d = str(tmp_path) + "/"
+    dl.write_synthetic_file(d, 1, num_utts=5, rawsize=12, outputDim=7, T_range=(5, 9), L_range=(2, 4))
+    loader = dl.DataLoader(d, 12, 8)                      # centre crop 12 -> 8 (dataLoader.py:62-67)
+    data_dict, alis, keys, sizes = loader.loadDataFileDict(1)
+    assert len(keys) == 5 and sizes.sum() == sum(v.shape[1] for v in data_dict.values())
+    raw = np.fromfile(d + "feats1.bin", np.float32).reshape(-1, 12)
+    k0 = keys[0]
+    assert data_dict[k0].shape == (8, sizes[0]) and data_dict[k0].dtype == np.float32
+    assert np.array_equal(data_dict[k0], raw[:sizes[0], 2:10].T)
+    assert all(1 <= int(x) < 7 for x in alis[k0])
+    loader.loadDataFileAsynch(1)
+    dd2, _, keys2, _ = loader.getDataAsynch()
+    assert keys2 == keys and np.array_equal(dd2[k0], data_dict[k0])
+
+
+def test_run_utils(tmp_path):
+    import run_utils
+    f = str(tmp_path / "cfg.json")
+    run_utils.dump_config({"b": 1, "a": [1, 2]}, f)
+    assert run_utils.load_config(f) == {"a": [1, 2], "b": 1}
+    assert run_utils.TimeString.match(str(run_utils.TimeString()))
+    s = run_utils.CfgStruct(x=3)
+    assert s.x == 3
+    run_utils.touch_file(str(tmp_path / "sentinel"))
+    assert os.path.exists(str(tmp_path / "sentinel"))
+
+
+def test_kaldi_header_format(tmp_path):
+    import writeLikelihoods as wl
+    f = str(tmp_path / "x.ark")
+    with open(f, "wb") as fid:
+        wl.writeUttHeader(fid, "utt1", 7, 35)
+    b = open(f, "rb").read()
+    assert b[:5] == b"utt1 " and b[5:6] == b"\x00" and b[6:10] == b"BFM "
+    assert struct.unpack("b", b[10:11])[0] == 4 and struct.unpack("i", b[11:15])[0] == 7
+    assert struct.unpack("b", b[15:16])[0] == 4 and struct.unpack("i", b[16:20])[0] == 35
+
+
+def test_shard_partitions_every_step():
+    import parallel
+    items = list(range(13))
+    for world in (1, 2, 3, 4, 8):
+        parts = [parallel.shard(items, r, world) for r in range(world)]
+        assert sorted(sum(parts, [])) == items
+        assert max(map(len, parts)) - min(map(len, parts)) <= 1
+        assert max(map(len, parts)) <= parallel.per_rank_capacity(len(items), world)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path[:0] = [ROOT, os.path.join(ROOT, "stanford-ctc_b200"), os.path.join(ROOT, "tests")]
+    import torch
+    import torch.distributed as dist
+    import parallel
+    import recipes
+    from oracle import brnn_oracle
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    d, r, w = parallel.world_info()
+    assert (r, w) == (rank, world)
+    datas, labelss = recipes.synth_batch(9, 7, [12, 15, 9, 14, 11], [3, 4, 2, 5, 3], seed=2)
+    np.random.seed(11)
+    nn = brnn_oracle.NNet(9, 7, 16, 2, 15, temporalLayer=1, dtype=np.float64)
+    nn.initParams()
+    # this rank's shard of the step, summed gradient flattened with the 4-float statistics tail
+    md, ml = parallel.shard(datas, rank, world), parallel.shard(labelss, rank, world)
+    costs, grad, skips = nn.costAndGradBatch(md, ml)
+    flat = np.concatenate([np.concatenate([g[0].ravel(), g[1].ravel()]) for g in grad] +
+                          [np.array([np.sum(~skips), costs[~skips].sum(), np.sum(skips), 0.0])])
+    t = torch.from_numpy(flat.copy())
+    parallel.allreduce_sum(d, t)
+    q.put((rank, t.numpy()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_data_parallel_reduction_world2_gloo():
+    """Two ranks (gloo, CPU): sharding + one all-reduce of the flat gradient reproduces the
+    single-process minibatch gradient and statistics."""
+    import torch.multiprocessing as mp
+    import recipes
+    from oracle import brnn_oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    datas, labelss = recipes.synth_batch(9, 7, [12, 15, 9, 14, 11], [3, 4, 2, 5, 3], seed=2)
+    np.random.seed(11)
+    nn = brnn_oracle.NNet(9, 7, 16, 2, 15, temporalLayer=1, dtype=np.float64)
+    nn.initParams()
+    costs, grad, skips = nn.costAndGradBatch(datas, labelss)
+    full = np.concatenate([np.concatenate([g[0].ravel(), g[1].ravel()]) for g in grad] +
+                          [np.array([5.0, costs.sum(), 0.0, 0.0])])
+    assert np.array_equal(res[0], res[1])                 # identical on every rank
+    np.testing.assert_allclose(res[0], full, rtol=1e-12, atol=1e-12)

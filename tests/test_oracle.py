@@ -1,0 +1,117 @@
+"""CPU tests: the oracle restatements against the reference's golden vectors (tests/golden, produced by
+the unmodified ctc_fast.pyx) and, where oracle/_ref is present, against the reference itself live."""
+import numpy as np
+import pytest
+
+import recipes
+from oracle import ctc_oracle, brnn_oracle
+
+REL = 1e-12
+
+
+def _run(name):
+    probs, seq = recipes.ctc_case(name)
+    return probs, seq, ctc_oracle.ctc_loss(np.asfortranarray(probs.astype(np.float64)), seq)
+
+
+@pytest.mark.parametrize("name", recipes.ALL_CTC)
+def test_c_restatement_matches_golden(name, golden_ctc):
+    probs, seq, (nll, grad, skip) = _run(name)
+    assert bool(golden_ctc[name + "/skip"]) == skip
+    if skip:
+        assert not grad.any()
+        return
+    g_nll = float(golden_ctc[name + "/nll"])
+    if np.isinf(g_nll):
+        assert np.isinf(nll)
+    else:
+        assert abs(nll - g_nll) <= REL * abs(g_nll)
+    st = recipes.golden_stride(*probs.shape)
+    np.testing.assert_allclose(grad[:, ::st], golden_ctc[name + "/grad"], rtol=0, atol=2e-7)  # stored as f32
+    assert abs(np.linalg.norm(grad) - float(golden_ctc[name + "/gradnorm"])) <= 1e-10
+
+
+def test_known_answer_time_trials():
+    """ctc/time_trials.py:13-25 recipe on float64 probs -> the value recorded in BASELINE.md."""
+    params, seq = recipes.time_trials()
+    nll, grad, skip = ctc_oracle.ctc_loss(np.asfortranarray(params), seq)
+    assert not skip
+    assert abs(nll - 1710.233966660) < 1e-6
+    assert abs(np.linalg.norm(grad) - 26.721212367) < 1e-6
+    assert np.abs(grad.sum(axis=0)).max() < 1e-12      # gradient columns sum to zero
+
+
+@pytest.mark.skipif(ctc_oracle.ref_module() is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", recipes.ALL_CTC)
+def test_c_restatement_matches_reference_live(name):
+    probs, seq, (nll, grad, skip) = _run(name)
+    r_nll, r_grad, r_skip = ctc_oracle.ref_ctc_loss(np.asfortranarray(probs.astype(np.float64)), seq)
+    assert skip == r_skip
+    if not skip:
+        assert (nll == r_nll) or (np.isinf(nll) and np.isinf(r_nll))
+        assert np.array_equal(grad, r_grad)          # bit-exact: same operation order in float64
+
+
+def test_reference_contract_errors():
+    p, s = recipes.ctc_case("c1")
+    with pytest.raises(ValueError):
+        ctc_oracle.ctc_loss(np.ascontiguousarray(p.astype(np.float64)), s)   # C-ordered: reference raises too
+
+
+def test_best_path_restatement():
+    probs = np.zeros((10, 9))
+    path = [0, 3, 3, 0, 3, 1, 5, 5, 8]         # labels 1 and 8 are dropped by the reference (:176-179)
+    probs[path, np.arange(9)] = 1.0
+    hyp, align = ctc_oracle.decode_best_path(np.asfortranarray(probs))
+    assert hyp == [3, 3, 5] and align == [2, 4, 7]
+    if ctc_oracle.ref_module() is not None:
+        rh, ra = ctc_oracle.ref_module().decode_best_path(np.asfortranarray(probs))
+        assert (list(rh), list(ra)) == (hyp, align)
+
+
+def test_brnn_restatement_matches_golden(golden_brnn):
+    cfg, data, labels = recipes.rnnetcpu()
+    np.random.seed(33); np.random.randn(20, 10)
+    nn = brnn_oracle.NNet(cfg["inputDim"], cfg["outputDim"], cfg["layerSize"], cfg["numLayers"], cfg["maxBatch"],
+                          temporalLayer=cfg["temporalLayer"], dtype=np.float64)
+    nn.initParams()
+    for i, (w, b) in enumerate(nn.stack):
+        assert np.array_equal(w.astype(np.float32), golden_brnn["rnnetcpu/w%d" % i])   # same draw order
+    cost, grad, skip = nn.costAndGrad(data.astype(np.float32), labels)
+    assert not skip and abs(cost - float(golden_brnn["rnnetcpu/cost"])) < 1e-9
+    for i, (dw, db) in enumerate(grad):
+        np.testing.assert_allclose(dw, golden_brnn["rnnetcpu/dw%d" % i], rtol=1e-9, atol=1e-12)
+
+
+def test_brnn_restatement_gradcheck():
+    """Finite-difference check of the restatement itself (tolerance of the reference's own check,
+    |analytic - numeric| <= 1e-4: rnnetcpu.py:165, ctc/gradcheck.py:40)."""
+    rng = np.random.RandomState(3)
+    np.random.seed(3)
+    nn = brnn_oracle.NNet(7, 5, 12, 3, 9, temporalLayer=2, dtype=np.float64, round_f32=False)
+    nn.initParams()
+    data = rng.randn(7, 9)
+    labels = np.array([1, 2, 2, 4], dtype=np.int32)
+    cost, grad, _ = nn.costAndGrad(data, labels)
+    grad = [[dw.copy(), db.copy()] for dw, db in grad]
+    eps = 1e-6
+    for pi, (w, b) in enumerate(nn.stack):
+        for _ in range(6):
+            i, j = rng.randint(w.shape[0]), rng.randint(w.shape[1])
+            w[i, j] += eps; cp = nn.costAndGrad(data, labels)[0]
+            w[i, j] -= 2 * eps; cm = nn.costAndGrad(data, labels)[0]
+            w[i, j] += eps
+            assert abs(grad[pi][0][i, j] - (cp - cm) / (2 * eps)) < 1e-4
+
+
+def test_brnn_float32_mode_close_to_float64():
+    datas, labelss = recipes.synth_batch(13, 11, [20, 17], [5, 4], seed=1)
+    outs = []
+    for dt in (np.float64, np.float32):
+        np.random.seed(5)
+        nn = brnn_oracle.NNet(13, 11, 32, 2, 20, temporalLayer=1, dtype=dt)
+        nn.initParams()
+        costs, grad, skips = nn.costAndGradBatch(datas, labelss)
+        outs.append((costs, np.concatenate([g[0].ravel() for g in grad]).astype(np.float64)))
+    assert np.allclose(outs[0][0], outs[1][0], rtol=1e-4)
+    assert np.linalg.norm(outs[0][1] - outs[1][1]) / np.linalg.norm(outs[0][1]) < 1e-4
