@@ -14,9 +14,9 @@
 //   * the T x K activations are streamed in TIME TILES of TT frames: a coalesced copy into shared
 //     memory, then the softmax statistics of all TT frames at once (2 lanes per frame, off the
 //     serial chain); the recurrence then gathers p[label] from the shared-memory tile.
-//   * alpha-tilde is spilled to a [T][2*32*P] fp32 workspace (coalesced float2 per pair) and read
-//     back, prefetched, by the beta sweep, which scatters alpha*beta into a shared-memory
-//     occupancy tile; the gradient of a whole tile is then written with coalesced row stores.
+//   * alpha-tilde is spilled to a [T][2*32*P] fp64 workspace (coalesced double2 per pair) and read
+//     back, prefetched, by the beta sweep, which scatters the normalised occupancies into a
+//     shared-memory tile; the gradient of a whole tile is then written with coalesced row stores.
 //
 // Scaling is arbitrary per frame (the gradient divides by absum[t], ctc_fast.pyx:133-145), so the
 // recurrences run on e = exp(x - max) and the log-partition is added to the loss separately.
@@ -35,25 +35,42 @@ struct CtcArgs {
     int B, Tmax, K, Kp, blank;
     float *grad, *nll;
     int32_t *skip;
-    float *ws;            // alpha-tilde spill: [B][Tmax][Lpad]
-    int64_t ws_utt;       // floats per utterance in ws
+    float *ws;            // alpha-tilde spill: [B][Tmax][Lpad] doubles
+    int64_t ws_utt;       // doubles per utterance in ws
 };
 
-// Load TT rows of activations into the shared tile and turn them into e = exp(x - rowmax).
-// Returns (in lane r < TT) Z_r = sum_k e[r][k]; rows beyond T are zero-filled with Z = 1.
-__device__ __forceinline__ float load_tile(const CtcArgs &a, const float *base, int t0, int T, float *te,
-                                           int lane) {
+// ---- asynchronous tile copy: global -> shared without staging registers (LDGSTS) ------------
+__device__ __forceinline__ void cp_async4(float *dst, const float *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Issue the copy of TT activation rows (frames t0 .. t0+TT-1) into a shared tile; rows beyond T are
+// zero-filled.  Coalesced: consecutive lanes fetch consecutive classes of one frame.
+__device__ __forceinline__ void issue_tile(const CtcArgs &a, const float *base, int t0, int T, float *te, int lane) {
     const int K = a.K, Kp = a.Kp;
-#pragma unroll 4
     for (int r = 0; r < TT; ++r) {
         const int t = t0 + r;
-        const float *row = base + (int64_t)t * a.fs;
-        for (int k = lane; k < K; k += 32) te[r * Kp + k] = (t < T) ? __ldg(row + k) : 0.f;
+        float *drow = te + r * Kp;
+        if (t < T) {
+            const float *row = base + (int64_t)t * a.fs;
+            for (int k = lane; k < K; k += 32) cp_async4(drow + k, row + k);
+        } else {
+            for (int k = lane; k < K; k += 32) drow[k] = 0.f;
+        }
     }
-    __syncwarp();
+    cp_async_commit();
+}
+
+// Turn a landed tile into e = exp(x - rowmax) in place; two lanes per frame (lane = r + 16 h).
+// Returns Z_r = sum_k e[r][k] in the lanes that own row r (1 for rows beyond T or probability input).
+__device__ __forceinline__ float tile_stats(const CtcArgs &a, int t0, int T, float *te, int lane) {
     float Z = 1.f;
     if (!a.is_prob) {
-        // two lanes per frame: lane = r + 16*h handles k = h, h+2, ...
+        const int K = a.K, Kp = a.Kp;
         const int r = lane & (TT - 1), h = lane >> 4;
         float *row = te + r * Kp;
         float m = -CUDART_INF_F;
@@ -61,7 +78,7 @@ __device__ __forceinline__ float load_tile(const CtcArgs &a, const float *base, 
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
         float z = 0.f;
         for (int k = h; k < K; k += 2) {
-            const float e = __expf(row[k] - m);
+            const float e = expf(row[k] - m);
             row[k] = e;
             z += e;
         }
@@ -72,6 +89,16 @@ __device__ __forceinline__ float load_tile(const CtcArgs &a, const float *base, 
     return Z;
 }
 
+__device__ __forceinline__ int dexp_field(double v) { return (__double2hiint(v) >> 20) & 0x7ff; }
+__device__ __forceinline__ double pow2_from_field(int biased) { return __hiloint2double(biased << 20, 0); }
+
+constexpr float GFIX = 1073741824.f;   // occupancies are accumulated as 2^30 fixed point (native ATOMS.ADD)
+
+// One warp per utterance.  alpha/beta live in registers in FLOAT64 (the reference's own arithmetic,
+// ctc_fast.pyx:23-37): float32 cannot hold the product of the alpha and beta tails, which is what the
+// gradient is made of.  Instead of dividing by the frame normaliser every frame (a warp reduction on
+// the serial chain) the state is rescaled by a power of two derived from the PREVIOUS frame's largest
+// exponent (one REDUX.MAX off the chain); the accumulated exponent goes into the loss.
 template <int P>
 __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
     extern __shared__ float smem[];
@@ -79,18 +106,18 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + wib;
     if (u >= a.B) return;
     const int K = a.K, Kp = a.Kp, blank = a.blank;
-    float *te = smem + (size_t)wib * 2 * TT * Kp;  // e tile
-    float *tg = te + TT * Kp;                      // occupancy tile
+    float *te0 = smem + (size_t)wib * 3 * TT * Kp;   // two e tiles (double buffer) ...
+    float *tg = te0 + 2 * TT * Kp;                   // ... and the occupancy tile
     const int T = min(a.Tlen[u], a.Tmax);
     const int lo = a.loff[u];
     const int nlab = a.loff[u + 1] - lo;
     const int L = 2 * nlab + 1;
     const float *base = a.acts + (int64_t)u * a.us;
     float *gbase = a.grad + (int64_t)u * a.us;
-    float *wsu = a.ws + (int64_t)u * a.ws_utt;
-    constexpr int LP = 64 * P;  // padded trellis row in the workspace
+    double *wsu = reinterpret_cast<double *>(a.ws) + (int64_t)u * a.ws_utt;
+    constexpr int LP = 64 * P;  // padded trellis row (doubles) in the workspace
 
-    // per-lane label data for pairs i = lane*P + j
+    // per-lane label data for pairs i = lane*P + j  (blank s = 2i, label s = 2i+1)
     int lab[P];
     bool allow_a[P], allow_b[P];
 #pragma unroll
@@ -105,180 +132,189 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
 
     const bool short_utt = (T < nlab);  // every window empty: reference returns (inf, p, False)
     bool fail = (T <= 0);
-    float mant = 1.f;   // running product of frame normalisers: mantissa ...
-    int expo = 0;       // ... and exponent
-    float logZ = 0.f;   // lane r accumulates log Z of the rows it owns
+    float logZ = 0.f;     // lanes < TT accumulate log Z of the rows they own
+    int S = 0;            // accumulated power-of-two scaling of alpha
+    double final_sum = 1.0;
+    const int ntiles = (T + TT - 1) / TT;
 
     // ------------------------------------------------------------------ alpha sweep (:42-76)
     if (!short_utt && !fail) {
-        float ab[P], al[P];
+        double ab[P], al[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) ab[j] = al[j] = 0.f;
-        for (int t0 = 0; t0 < T && !fail; t0 += TT) {
-            const float Z = load_tile(a, base, t0, T, te, lane);
+        for (int j = 0; j < P; ++j) ab[j] = al[j] = 0.0;
+        int kscale = 0;   // power of two applied to the next frame
+        issue_tile(a, base, 0, T, te0, lane);
+        for (int tile = 0; tile < ntiles && !fail; ++tile) {
+            const int t0 = tile * TT;
+            float *te = te0 + (tile & 1) * TT * Kp;
+            if (tile + 1 < ntiles) {
+                issue_tile(a, base, t0 + TT, T, te0 + ((tile + 1) & 1) * TT * Kp, lane);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const float Z = tile_stats(a, t0, T, te, lane);
             if (lane < TT) logZ += logf(Z);
             const int rmax = min(TT, T - t0);
             for (int r = 0; r < rmax; ++r) {
                 const int t = t0 + r;
                 const float *row = te + r * Kp;
-                const float eb = row[blank];
-                float nb[P], nl[P], csum = 0.f;
-                if (t == 0) {
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const int i = lane * P + j;
-                        nb[j] = (i == 0) ? eb : 0.f;
-                        nl[j] = (i == 0 && nlab > 0) ? row[lab[j]] : 0.f;
-                        csum += nb[j] + nl[j];
-                    }
-                } else {
-                    int start = 2 * (T - t);
-                    start = (L <= start) ? 0 : L - start;
-                    float pl = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-                    if (lane == 0) pl = 0.f;
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const int i = lane * P + j;
-                        const float el = (lab[j] >= 0) ? row[lab[j]] : 0.f;
-                        float b = (ab[j] + pl) * eb;
-                        float l = (al[j] + ab[j] + (allow_a[j] ? pl : 0.f)) * el;
-                        if (2 * i < start || i > nlab) b = 0.f;
-                        if (2 * i + 1 < start) l = 0.f;
-                        pl = al[j];
-                        nb[j] = b;
-                        nl[j] = l;
-                        csum += b + l;
-                    }
-                }
-                const float c = warp_sum(csum);
-                if (c == 0.f) { fail = true; break; }
-                const float inv = 1.f / c;
-                int e2;
-                mant *= frexpf(c, &e2);
-                expo += e2;
-                int e3;
-                mant = frexpf(mant, &e3);
-                expo += e3;
-                float2 *wrow = reinterpret_cast<float2 *>(wsu + (int64_t)t * LP) + lane * P;
+                const double eb = (double)row[blank];
+                int start = 2 * (T - t);
+                start = (t == 0 || L <= start) ? 0 : L - start;
+                double pl = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+                if (lane == 0) pl = 0.0;
+                const double sc = pow2_from_field(1023 + kscale);
+                double mx = 0.0;
 #pragma unroll
                 for (int j = 0; j < P; ++j) {
-                    ab[j] = nb[j] * inv;
-                    al[j] = nl[j] * inv;
-                    wrow[j] = make_float2(ab[j], al[j]);
+                    const int i = lane * P + j;
+                    const double el = (lab[j] >= 0) ? (double)row[lab[j]] : 0.0;
+                    double b = (ab[j] + pl) * eb;
+                    double l = (al[j] + ab[j] + (allow_a[j] ? pl : 0.0)) * el;
+                    if (t == 0) {                       // :42-47
+                        b = (i == 0) ? eb : 0.0;
+                        l = (i == 0) ? el : 0.0;
+                    }
+                    if (2 * i < start || i > nlab) b = 0.0;
+                    if (2 * i + 1 < start) l = 0.0;
+                    pl = al[j];
+                    ab[j] = b * sc;
+                    al[j] = l * sc;
+                    mx = fmax(mx, fmax(ab[j], al[j]));
                 }
+                S += kscale;
+                const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
+                if (emax == 0) { fail = true; break; }      // all mass gone: ZeroDivisionError in :70-76
+                kscale = 1023 - emax;
+                double2 *wrow = reinterpret_cast<double2 *>(wsu + (int64_t)t * LP) + lane * P;
+#pragma unroll
+                for (int j = 0; j < P; ++j) wrow[j] = make_double2(ab[j], al[j]);
             }
             __syncwarp();
+        }
+        if (!fail) {   // p(l|x) = alpha[L-1] + alpha[L-2] at the last frame
+            double fs = 0.0;
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const int i = lane * P + j;
+                if (i == nlab) fs += ab[j];
+                if (i == nlab - 1) fs += al[j];
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
+            final_sum = fs;
+            if (!(fs > 0.0)) fail = true;
         }
     }
 
     // ------------------------------------------------------------------ beta sweep + gradient
-    float my_absum = 0.f, my_Zinv = 1.f;
+    float my_Zinv = 1.f;
     if (!fail) {
-        float bb[P], bl[P];
+        double bb[P], bl[P];
 #pragma unroll
-        for (int j = 0; j < P; ++j) bb[j] = bl[j] = 0.f;
-        const int ntiles = (T + TT - 1) / TT;
+        for (int j = 0; j < P; ++j) bb[j] = bl[j] = 0.0;
+        int kscale = 0;
+        issue_tile(a, base, (ntiles - 1) * TT, T, te0 + ((ntiles - 1) & 1) * TT * Kp, lane);
         for (int tile = ntiles - 1; tile >= 0 && !fail; --tile) {
             const int t0 = tile * TT;
-            const float Z = load_tile(a, base, t0, T, te, lane);
+            float *te = te0 + (tile & 1) * TT * Kp;
+            if (tile > 0) {
+                issue_tile(a, base, t0 - TT, T, te0 + ((tile - 1) & 1) * TT * Kp, lane);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            __syncwarp();
+            const float Z = tile_stats(a, t0, T, te, lane);
             my_Zinv = 1.f / Z;
-            my_absum = 0.f;
-            for (int idx = lane; idx < TT * Kp; idx += 32) tg[idx] = 0.f;
+            unsigned *tgu = reinterpret_cast<unsigned *>(tg);
+            for (int idx = lane; idx < TT * Kp; idx += 32) tgu[idx] = 0u;
             __syncwarp();
             const int rmax = min(TT, T - t0);
             if (!short_utt) {
-                // prefetch alpha-tilde of the first frame of this tile's sweep
-                float2 an[P];
+                double2 an[P];   // alpha-tilde of the next frame to be processed (prefetched)
                 {
-                    const float2 *arow = reinterpret_cast<const float2 *>(wsu + (int64_t)(t0 + rmax - 1) * LP) + lane * P;
+                    const double2 *arow = reinterpret_cast<const double2 *>(wsu + (int64_t)(t0 + rmax - 1) * LP) + lane * P;
 #pragma unroll
                     for (int j = 0; j < P; ++j) an[j] = arow[j];
                 }
                 for (int r = rmax - 1; r >= 0; --r) {
                     const int t = t0 + r;
                     const float *row = te + r * Kp;
-                    float *grow = tg + r * Kp;
-                    const float eb = row[blank];
-                    float2 av[P];
+                    unsigned *grow = tgu + r * Kp;
+                    const double eb = (double)row[blank];
+                    double2 av[P];
 #pragma unroll
                     for (int j = 0; j < P; ++j) av[j] = an[j];
-                    if (t > 0) {  // prefetch next (earlier) frame; crosses into the previous tile's rows
-                        const float2 *arow = reinterpret_cast<const float2 *>(wsu + (int64_t)(t - 1) * LP) + lane * P;
+                    {   // prefetch the earlier frame (t-1, clamped: the value is unused at t = 0)
+                        const int tp = max(t - 1, 0);
+                        const double2 *arow = reinterpret_cast<const double2 *>(wsu + (int64_t)tp * LP) + lane * P;
 #pragma unroll
                         for (int j = 0; j < P; ++j) an[j] = arow[j];
                     }
-                    float nb[P], nl[P], el[P], csum = 0.f;
-                    if (t == T - 1) {   // :78-83
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int i = lane * P + j;
-                            el[j] = (lab[j] >= 0) ? row[lab[j]] : 0.f;
-                            nb[j] = (i == nlab) ? eb : 0.f;
-                            nl[j] = (i == nlab - 1) ? el[j] : 0.f;
-                            csum += nb[j] + nl[j];
-                        }
-                    } else {            // :84-114
-                        const int end = min(2 * t + 2, L);
-                        float nxb = __shfl_down_sync(0xffffffffu, bb[0], 1);
-                        float nxl = __shfl_down_sync(0xffffffffu, bl[0], 1);
-                        if (lane == 31) nxb = nxl = 0.f;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) {
-                            const int i = lane * P + j;
-                            el[j] = (lab[j] >= 0) ? row[lab[j]] : 0.f;
-                            const float b1 = (j + 1 < P) ? bb[(j + 1 < P) ? j + 1 : j] : nxb;
-                            const float l1 = (j + 1 < P) ? bl[(j + 1 < P) ? j + 1 : j] : nxl;
-                            float b = (bb[j] + bl[j]) * eb;
-                            float l = (bl[j] + b1 + (allow_b[j] ? l1 : 0.f)) * el[j];
-                            if (2 * i >= end || i > nlab) b = 0.f;
-                            if (2 * i + 1 >= end) l = 0.f;
-                            nb[j] = b;
-                            nl[j] = l;
-                            csum += b + l;
-                        }
-                    }
-                    // occupancy numerators on the UNscaled beta; one interleaved butterfly for
-                    // (normaliser, blank occupancy, absum)
-                    float sb = 0.f, sa = 0.f, abl[P];
+                    const int end = (t == T - 1) ? L : min(2 * t + 2, L);
+                    double nxb = __shfl_down_sync(0xffffffffu, bb[0], 1);
+                    double nxl = __shfl_down_sync(0xffffffffu, bl[0], 1);
+                    if (lane == 31) nxb = nxl = 0.0;
+                    const double sc = pow2_from_field(1023 + kscale);
+                    double nb[P], nl[P], w = 0.0, wb = 0.0, mx = 0.0;
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
-                        const float x = av[j].x * nb[j];
-                        abl[j] = av[j].y * nl[j];
-                        sb += x;
-                        if (x != 0.f) sa += x / eb;                   // :122-125
-                        if (abl[j] != 0.f) sa += abl[j] / el[j];      // :127-131
+                        const int i = lane * P + j;
+                        const double el = (lab[j] >= 0) ? (double)row[lab[j]] : 0.0;
+                        const double b1 = (j + 1 < P) ? bb[(j + 1 < P) ? j + 1 : j] : nxb;
+                        const double l1 = (j + 1 < P) ? bl[(j + 1 < P) ? j + 1 : j] : nxl;
+                        // pre-emission sums: beta[s,t] = pre[s] * p[lab(s),t]
+                        double pb = bb[j] + bl[j];
+                        double pll = bl[j] + b1 + (allow_b[j] ? l1 : 0.0);
+                        if (t == T - 1) {               // :78-83
+                            pb = (i == nlab) ? 1.0 : 0.0;
+                            pll = (i == nlab - 1) ? 1.0 : 0.0;
+                        }
+                        if (2 * i >= end || i > nlab) pb = 0.0;
+                        if (2 * i + 1 >= end || lab[j] < 0) pll = 0.0;
+                        pb *= sc;
+                        pll *= sc;
+                        // occupancy numerators alpha*beta/p = alpha * pre  (no division by p, :117-136)
+                        const double wbj = av[j].x * pb;
+                        nl[j] = av[j].y * pll;          // reuse nl[] for the label numerators
+                        wb += wbj;
+                        w += wbj + nl[j];
+                        nb[j] = pb * eb;
+                        const double lnew = pll * el;
+                        mx = fmax(mx, fmax(nb[j], lnew));
+                        bl[j] = lnew;                   // old bl[j] no longer needed by later j
                     }
+#pragma unroll
+                    for (int j = 0; j < P; ++j) bb[j] = nb[j];
+                    const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
+                    kscale = 1023 - emax;
+                    // absum and the blank occupancy: one interleaved butterfly (off the recurrence chain)
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) {
-                        csum += __shfl_xor_sync(0xffffffffu, csum, o);
-                        sb += __shfl_xor_sync(0xffffffffu, sb, o);
-                        sa += __shfl_xor_sync(0xffffffffu, sa, o);
+                        w += __shfl_xor_sync(0xffffffffu, w, o);
+                        wb += __shfl_xor_sync(0xffffffffu, wb, o);
                     }
-                    if (csum == 0.f) { fail = true; break; }
-                    const float inv = 1.f / csum;
+                    if (emax == 0 || !(w > 0.0)) { fail = true; break; }
+                    const double winv = 1.0 / w;
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
-                        bb[j] = nb[j] * inv;
-                        bl[j] = nl[j] * inv;
-                        if (abl[j] != 0.f) atomicAdd(grow + lab[j], abl[j] * inv);
+                        const float g = (float)(nl[j] * winv);
+                        if (g > 0.f) atomicAdd(grow + lab[j], (unsigned)(g * GFIX + 0.5f));
                     }
-                    if (lane == 0) atomicAdd(grow + blank, sb * inv);
-                    if (lane == r) my_absum = sa * inv;
+                    if (lane == 0) atomicAdd(grow + blank, (unsigned)((float)(wb * winv) * GFIX + 0.5f));
                 }
             }
             __syncwarp();
             if (fail) break;
-            // tile epilogue: grad = p - G/(e*absum)  (:139-145), coalesced row stores
+            // tile epilogue: grad = p - occupancy (:139-145), coalesced row stores
             for (int r = 0; r < rmax; ++r) {
-                const float absum = __shfl_sync(0xffffffffu, my_absum, r);
                 const float zinv = __shfl_sync(0xffffffffu, my_Zinv, r);
                 float *orow = gbase + (int64_t)(t0 + r) * a.fs;
-                for (int k = lane; k < K; k += 32) {
-                    const float e = te[r * Kp + k];
-                    const float tmp = e * absum;
-                    const float p = e * zinv;
-                    orow[k] = (tmp > 0.f) ? p - tg[r * Kp + k] / tmp : p;
-                }
+                for (int k = lane; k < K; k += 32)
+                    orow[k] = te[r * Kp + k] * zinv - (float)tgu[r * Kp + k] * (1.f / GFIX);
             }
             __syncwarp();
         }
@@ -299,7 +335,7 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
     if (lane == 0) {
         float nll;
         if (short_utt && !fail) nll = CUDART_INF_F;
-        else nll = -(logf(mant) + (float)expo * 0.69314718055994531f - lz);
+        else nll = (float)(-(log(final_sum) - (double)S * 0.69314718055994530942 - (double)lz));
         a.nll[u] = nll;
         a.skip[u] = fail ? 1 : 0;
     }
@@ -358,7 +394,7 @@ using namespace ctcb;
 extern "C" size_t ctcb_ctc_workspace_bytes(int B, int Tmax, int max_labels) {
     const int P = pairs_per_lane(max_labels);
     if (P == 0 || B <= 0 || Tmax <= 0) return 0;
-    return (size_t)B * (size_t)Tmax * (size_t)(64 * P) * sizeof(float);
+    return (size_t)B * (size_t)Tmax * (size_t)(64 * P) * sizeof(double);
 }
 
 extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t utt_stride, int64_t frame_stride,
@@ -385,9 +421,9 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     a.grad = grad_out; a.nll = nll_out; a.skip = skip_out;
     a.ws = (float *)workspace; a.ws_utt = (int64_t)Tmax * 64 * P;
 
-    const size_t per_warp = (size_t)2 * TT * a.Kp * sizeof(float);
+    const size_t per_warp = (size_t)3 * TT * a.Kp * sizeof(float);
     int wpb = 8;
-    while (wpb > 1 && per_warp * wpb > 72 * 1024) wpb >>= 1;
+    while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > 200 * 1024)
         return set_error(CTCB_EINVAL, "ctcb_ctc_loss_grad_f32: K=%d too large for the shared-memory tile", K);

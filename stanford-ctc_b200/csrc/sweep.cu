@@ -11,10 +11,14 @@
 // 32 output units; lane l of warp w keeps W[j][l + 32 i] for its 4 rows j in registers for the
 // whole sweep (H/32 * 4 registers), so a time step only moves the previous hidden state
 // (8 utterances x H floats, read from L2 into shared memory) and the 32 x 8 new outputs.  Both
-// directions run concurrently in the same launch (blockIdx.z).  CTAs that share a (direction,
-// utterance partition) synchronise once per time step through a monotonically increasing counter
-// in global memory (cooperative launch guarantees co-residency); the hidden state itself is
-// exchanged through the output array in L2 (ld.global.cg), which has to be written anyway.
+// directions run concurrently in the same launch (blockIdx.z).
+//
+// There is NO barrier between time steps.  The hidden state is exchanged through the output array
+// itself (it has to be written anyway) with a flag-in-data protocol: the array is pre-filled with a
+// sentinel bit pattern (0xffffffff, a NaN no arithmetic produces), producers overwrite it with plain
+// stores, and consumers poll their operand loads (ld.volatile, L2) until no word is the sentinel.
+// One L2 round trip per step replaces fence + atomic + poll + load of a counter barrier, and CTAs run
+// as a decoupled dataflow pipeline (cooperative launch guarantees the co-residency polling needs).
 //
 // Data layout: time-major [T][B][H] fp32, so one time step of all utterances is contiguous.
 #include "common.cuh"
@@ -35,20 +39,25 @@ struct SweepArgs {
     const float *act[2];    // mode 1: For, Back (for the within(0,maxAct) masks)
     float maxAct;
     int parts;              // utterance partitions (gridDim.y)
-    unsigned int *counters; // [2 * parts], zeroed before launch
+    unsigned int *counters; // [0]: sticky poll-timeout flag, zeroed before launch
 };
 
-__device__ __forceinline__ void domain_barrier(unsigned int *ctr, unsigned int target) {
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(ctr, 1u);
-        unsigned int v;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-        } while (v < target);
-    }
-    __syncthreads();
+constexpr unsigned SENTINEL = 0xffffffffu;
+constexpr int POLL_LIMIT = 1 << 22;   // ~1 s of polling: a lost producer becomes an error flag, not a hang
+
+__device__ __forceinline__ float4 ld_volatile4(const float *p) {
+    float4 v;
+    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_volatile1(const float *p) {
+    float v;
+    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool is_sentinel(float x) { return __float_as_uint(x) == SENTINEL; }
+__device__ __forceinline__ bool any_sentinel(const float4 &v) {
+    return is_sentinel(v.x) || is_sentinel(v.y) || is_sentinel(v.z) || is_sentinel(v.w);
 }
 
 // KI > 0: H == 32*KI and the weights live in registers.  KI == 0: any H, weights re-read through L1/L2.
@@ -81,8 +90,6 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
     const int tiles_per_part = (ntiles + a.parts - 1) / a.parts;
     const int tile_beg = blockIdx.y * tiles_per_part;
     const int tile_end = min(ntiles, tile_beg + tiles_per_part);
-    unsigned int *ctr = a.counters + (dir * a.parts + blockIdx.y);
-    const unsigned int nslices = gridDim.x;
 
     // lane -> (row r, utterance b) of the value it ends up owning after the transposing reduction
     const int orow = lane >> 3, ob = lane & 7;
@@ -111,17 +118,57 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                 // previous state of this tile's utterances: [SW_NB][H] from L2 -> shared
                 const float *src = out + ((int64_t)tprev * B + b0) * H;
                 const int nb = min(SW_NB, B - b0);
-                if ((H & 3) == 0) {
+                if (KI >= 4) {
+                    // all operand loads in flight at once, then re-poll only the words still unwritten
+                    constexpr int NCH = (KI >= 4) ? KI / 4 : 1;     // float4 chunks per thread: 8*H/4/256
                     const int h4 = H >> 2;
-                    for (int idx = threadIdx.x; idx < nb * h4; idx += SW_THREADS) {
+                    float4 v[NCH];
+                    const float *p[NCH];
+                    bool need[NCH];
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int idx = threadIdx.x + c * SW_THREADS;
                         const int bb = idx / h4, k4 = idx - bb * h4;
-                        const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (int64_t)bb * H) + k4);
-                        *reinterpret_cast<float4 *>(hs + bb * Hp + 4 * k4) = v;
+                        need[c] = bb < nb;
+                        p[c] = src + (int64_t)bb * H + 4 * k4;
+                        v[c] = need[c] ? ld_volatile4(p[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                    int spins = 0;
+                    bool pending = true;
+                    while (pending) {
+                        pending = false;
+#pragma unroll
+                        for (int c = 0; c < NCH; ++c)
+                            if (need[c] && any_sentinel(v[c])) {      // producer has not stored this word yet
+                                v[c] = ld_volatile4(p[c]);
+                                pending = true;
+                            }
+                        if (pending && ((++spins & 63) == 0) &&
+                            (spins > POLL_LIMIT || *(volatile unsigned int *)a.counters != 0u)) {
+                            atomicExch(a.counters, 1u);
+                            break;
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c) {
+                        const int idx = threadIdx.x + c * SW_THREADS;
+                        const int bb = idx / h4, k4 = idx - bb * h4;
+                        if (need[c]) *reinterpret_cast<float4 *>(hs + bb * Hp + 4 * k4) = v[c];
                     }
                 } else {
                     for (int idx = threadIdx.x; idx < nb * H; idx += SW_THREADS) {
                         const int bb = idx / H, k = idx - bb * H;
-                        hs[bb * Hp + k] = __ldcg(src + (int64_t)bb * H + k);
+                        const float *p = src + (int64_t)bb * H + k;
+                        float v = ld_volatile1(p);
+                        int spins = 0;
+                        while (is_sentinel(v)) {
+                            if (++spins > POLL_LIMIT || *(volatile unsigned int *)a.counters != 0u) {
+                                atomicExch(a.counters, 1u);
+                                break;
+                            }
+                            v = ld_volatile1(p);
+                        }
+                        hs[bb * Hp + k] = v;
                     }
                 }
                 for (int idx = threadIdx.x + nb * Hp; idx < SW_NB * Hp; idx += SW_THREADS) hs[idx] = 0.f;
@@ -177,10 +224,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                     v = (act_v > 0.f && act_v < a.maxAct) ? v : 0.f;   // within(0, maxAct)
                     if (t >= Tb) v = 0.f;
                 }
+                if (is_sentinel(v)) v = __uint_as_float(0x7fc00000u);   // a NaN result must not look unwritten
                 out[((int64_t)t * B + b) * H + oj] = v;
             }
         }
-        if (s + 1 < T) domain_barrier(ctr, nslices * (unsigned int)(s + 1));
     }
 }
 
@@ -204,7 +251,10 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     if (parts > ntiles) parts = ntiles;
     if (parts < 1) parts = 1;
     a.parts = parts;
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 2 * parts, st));
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 4, st));
+    const size_t slab = sizeof(float) * (size_t)a.T * a.B * a.H;
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.out[0], 0xff, slab, st));     // sentinel = "not produced yet"
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.out[1], 0xff, slab, st));
     dim3 grid(slices, parts, 2);
     void *params[] = {&a};
     CTCB_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)sweep_kernel<KI>, grid, dim3(SW_THREADS), params, smem, st));

@@ -125,11 +125,16 @@ def run(args=None):
             cfg[key] = default
 
     # Logging
-    logging.basicConfig(filename=pjoin(output_dir, 'train.log' if rank == 0 else 'train.%d.log' % rank),
-                        level=logging.DEBUG)
     logger = logging.getLogger()
+    logger.setLevel(logging.DEBUG)
+    for h in [h for h in logger.handlers if getattr(h, '_ctcb', False)]:
+        logger.removeHandler(h)
+    handlers = [logging.FileHandler(pjoin(output_dir, 'train.log' if rank == 0 else 'train.%d.log' % rank))]
     if not cfg['quiet']:
-        logger.addHandler(logging.StreamHandler())
+        handlers.append(logging.StreamHandler())
+    for h in handlers:
+        h._ctcb = True
+        logger.addHandler(h)
     logger.info('Running on %s' % cfg['host'])
 
     # seed for debugging, turn off when stable                       runNNet.py:113-115
