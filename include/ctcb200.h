@@ -121,6 +121,16 @@ int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_p
                             float *regcost_out, float *probs_out, float *stats_out,
                             void *workspace, size_t ws_bytes, void *stream);
 
+/* ---- the time recurrences of the temporal layer on their own (replaces the per-frame loops
+ *      brnnet.py:144-152 [mode 0] and brnnet.py:208-224 [mode 1]) -------------------------------
+ * All arrays time-major [T][B][H] fp32.  mode 0: outF[t] = clip(pre[t] + outF[t-1].Wf^T, 0, maxAct),
+ * outB mirrored in time with Wb; utterance u is zero beyond T_per_utt[u].
+ * mode 1: outF[t] = within(actF[t]) * (pre[t] + outF[t+1].Wf), outB mirrored.
+ * scratch: >= 4096 bytes of device memory (error flag + diagnostics). */
+int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
+                        const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
+                        const float *actB, float maxAct, void *scratch, void *stream);
+
 /* ---- optimiser (replaces sgd.SGD.run arithmetic, ctc_fast/sgd.py:91-161, and
  *      NNet.updateParams, brnnet.py:251-256) --------------------------------------------------- */
 /* w += scale * u over n floats (updateParams) */

@@ -190,7 +190,7 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
     w.gemm = take(g);
     w.colsum = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
     w.scratch = take(8192);
-    w.counters = take(sizeof(unsigned int) * 2 * ((c->maxB + 7) / 8 + 1));
+    w.counters = take(sizeof(unsigned int) * 1024);
     w.total = off;
     return w;
 }
@@ -221,6 +221,17 @@ extern "C" void ctcb_brnn_destroy(ctcb_brnn *h) { delete h; }
         int _rc = (expr);            \
         if (_rc != CTCB_OK) return _rc; \
     } while (0)
+
+extern "C" int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
+                                   const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
+                                   const float *actB, float maxAct, void *scratch, void *stream) {
+    if (!T_per_utt || !pre || !Wf || !Wb || !outF || !outB || !scratch || (mode == 1 && (!actF || !actB)))
+        return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: null pointer argument");
+    if (T <= 0 || B <= 0 || H <= 0 || (mode != 0 && mode != 1))
+        return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: bad sizes");
+    return run_sweep(mode, T, B, H, T_per_utt, pre, Wf, Wb, outF, outB, actF, actB, maxAct,
+                     (unsigned int *)scratch, (cudaStream_t)stream);
+}
 
 extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_per_utt,
                                        const int32_t *labels, const int32_t *label_off, int B, int Tmax,

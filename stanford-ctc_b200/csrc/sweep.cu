@@ -14,14 +14,16 @@
 // directions run concurrently in the same launch (blockIdx.z).
 //
 // There is NO barrier between time steps.  The hidden state is exchanged through the output array
-// itself (it has to be written anyway) with a flag-in-data protocol: the array is pre-filled with a
-// sentinel bit pattern (0xffffffff, a NaN no arithmetic produces), producers overwrite it with plain
-// stores, and consumers poll their operand loads (ld.volatile, L2) until no word is the sentinel.
+// itself (it has to be written anyway) with a flag-in-data protocol: the producers pre-fill their own
+// words with a sentinel bit pattern (0xffffffff, a NaN no arithmetic produces; one grid barrier at
+// kernel start orders the fills), then overwrite them with
+// st.relaxed.gpu, and consumers poll their operand loads (ld.acquire.gpu) until no word is the sentinel.
 // One L2 round trip per step replaces fence + atomic + poll + load of a counter barrier, and CTAs run
 // as a decoupled dataflow pipeline (cooperative launch guarantees the co-residency polling needs).
 //
 // Data layout: time-major [T][B][H] fp32, so one time step of all utterances is contiguous.
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace ctcb {
 
@@ -43,17 +45,30 @@ struct SweepArgs {
 };
 
 constexpr unsigned SENTINEL = 0xffffffffu;
-constexpr int POLL_LIMIT = 1 << 22;   // ~1 s of polling: a lost producer becomes an error flag, not a hang
+constexpr long long POLL_CYCLES = 1000000000LL;   // ~0.5 s of polling: a lost producer becomes an error flag, not a hang
 
+__device__ __forceinline__ float4 ld_relaxed4(const float *p) {
+    float4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// Re-polls must be ACQUIRE loads: a relaxed gpu-scope load can keep hitting the SM's stale L1 copy of
+// a line it fetched while the producer was still writing it (measured on B200: the poll never sees the
+// update); the acquire's CCTL.IVALL drops that copy.  A stale copy only ever holds sentinel-or-final
+// words, so a word that does not read as the sentinel is always the final value.
 __device__ __forceinline__ float4 ld_volatile4(const float *p) {
     float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ float ld_volatile1(const float *p) {
     float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
+}
+// Strong (gpu-scope, relaxed) store: a weak st.global may linger in the SM and race with the polls.
+__device__ __forceinline__ void st_relaxed_gpu(float *p, float v) {
+    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 __device__ __forceinline__ bool is_sentinel(float x) { return __float_as_uint(x) == SENTINEL; }
 __device__ __forceinline__ bool any_sentinel(const float4 &v) {
@@ -95,6 +110,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
     const int orow = lane >> 3, ob = lane & 7;
     const int oj = j0 + orow;
 
+    // Sentinel pre-fill by the producers themselves: every lane marks the words it will produce later
+    // as "not produced yet", then ONE grid-wide barrier (the only one of the sweep) orders all fills
+    // before any poll.  Same-thread program order then guarantees fill-before-produce.
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int b = tile * SW_NB + ob;
+        if (oj < H && b < B)
+            for (int t = 0; t < T; ++t) st_relaxed_gpu(out + ((int64_t)t * B + b) * H + oj, __uint_as_float(SENTINEL));
+    }
+    __threadfence();
+    cooperative_groups::this_grid().sync();
+
     for (int s = 0; s < T; ++s) {
         const int t = ascending ? s : T - 1 - s;
         const int tprev = ascending ? t - 1 : t + 1;
@@ -131,22 +157,29 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                         const int bb = idx / h4, k4 = idx - bb * h4;
                         need[c] = bb < nb;
                         p[c] = src + (int64_t)bb * H + 4 * k4;
-                        v[c] = need[c] ? ld_volatile4(p[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v[c] = need[c] ? ld_relaxed4(p[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                     int spins = 0;
-                    bool pending = true;
-                    while (pending) {
-                        pending = false;
+                    bool dead = false;
+                    long long t_start = 0;
 #pragma unroll
-                        for (int c = 0; c < NCH; ++c)
-                            if (need[c] && any_sentinel(v[c])) {      // producer has not stored this word yet
-                                v[c] = ld_volatile4(p[c]);
-                                pending = true;
+                    for (int c = 0; c < NCH; ++c) {
+                        while (need[c] && !dead && any_sentinel(v[c])) {   // producer has not stored this word yet
+                            if (spins == 0) t_start = clock64();
+                            if (((++spins & 63) == 0) &&
+                                (clock64() - t_start > POLL_CYCLES || *(volatile unsigned int *)a.counters != 0u)) {
+                                if (atomicCAS(a.counters, 0u, 1u) == 0u) {   // first timeout: who waited for what
+                                    a.counters[3] = (unsigned)s; a.counters[4] = blockIdx.x; a.counters[5] = blockIdx.y;
+                                    a.counters[6] = blockIdx.z; a.counters[7] = (unsigned)c; a.counters[8] = threadIdx.x;
+                                    a.counters[9] = (unsigned)tprev;
+                                }
+                                atomicAdd(a.counters + 2, 1u);
+                                if (threadIdx.x == 0 || a.counters[16 + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] == 0u)
+                                    a.counters[16 + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 1000u + (unsigned)s;
+                                dead = true;
+                                break;
                             }
-                        if (pending && ((++spins & 63) == 0) &&
-                            (spins > POLL_LIMIT || *(volatile unsigned int *)a.counters != 0u)) {
-                            atomicExch(a.counters, 1u);
-                            break;
+                            v[c] = ld_volatile4(p[c]);
                         }
                     }
 #pragma unroll
@@ -161,8 +194,11 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                         const float *p = src + (int64_t)bb * H + k;
                         float v = ld_volatile1(p);
                         int spins = 0;
+                        long long t_start = 0;
                         while (is_sentinel(v)) {
-                            if (++spins > POLL_LIMIT || *(volatile unsigned int *)a.counters != 0u) {
+                            if (spins == 0) t_start = clock64();
+                            if (((++spins & 63) == 0) &&
+                                (clock64() - t_start > POLL_CYCLES || *(volatile unsigned int *)a.counters != 0u)) {
                                 atomicExch(a.counters, 1u);
                                 break;
                             }
@@ -225,7 +261,7 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                     if (t >= Tb) v = 0.f;
                 }
                 if (is_sentinel(v)) v = __uint_as_float(0x7fc00000u);   // a NaN result must not look unwritten
-                out[((int64_t)t * B + b) * H + oj] = v;
+                st_relaxed_gpu(out + ((int64_t)t * B + b) * H + oj, v);
             }
         }
     }
@@ -251,10 +287,7 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     if (parts > ntiles) parts = ntiles;
     if (parts < 1) parts = 1;
     a.parts = parts;
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 4, st));
-    const size_t slab = sizeof(float) * (size_t)a.T * a.B * a.H;
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.out[0], 0xff, slab, st));     // sentinel = "not produced yet"
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.out[1], 0xff, slab, st));
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 1024, st));
     dim3 grid(slices, parts, 2);
     void *params[] = {&a};
     CTCB_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)sweep_kernel<KI>, grid, dim3(SW_THREADS), params, smem, st));
