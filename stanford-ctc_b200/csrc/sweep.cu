@@ -7,23 +7,24 @@
 //             (brnnet.py:208-224: mvdot_col_slice on W.T + mult_slice)
 // with a batch of utterances as the second matrix dimension.
 //
+// Two kernels share this design point:
+//   * sweep_cluster.cu (H = 128/256/512): one thread-block cluster per (direction, 8 utterances); the
+//     hidden state is exchanged CTA-to-CTA through distributed shared memory with bulk async copies
+//     that complete on the consumer's mbarrier -- no global-memory round trip on the serial chain.
+//   * this file (any H): the general fallback below, exchanging through L2 with a counter barrier.
+//
 // Design (B200): the H x H recurrent matrix never leaves the register file.  A CTA of 8 warps owns
 // 32 output units; lane l of warp w keeps W[j][l + 32 i] for its 4 rows j in registers for the
 // whole sweep (H/32 * 4 registers), so a time step only moves the previous hidden state
 // (8 utterances x H floats, read from L2 into shared memory) and the 32 x 8 new outputs.  Both
-// directions run concurrently in the same launch (blockIdx.z).
-//
-// There is NO barrier between time steps.  The hidden state is exchanged through the output array
-// itself (it has to be written anyway) with a flag-in-data protocol: the producers pre-fill their own
-// words with a sentinel bit pattern (0xffffffff, a NaN no arithmetic produces; one grid barrier at
-// kernel start orders the fills), then overwrite them with
-// st.relaxed.gpu, and consumers poll their operand loads (ld.acquire.gpu) until no word is the sentinel.
-// One L2 round trip per step replaces fence + atomic + poll + load of a counter barrier, and CTAs run
-// as a decoupled dataflow pipeline (cooperative launch guarantees the co-residency polling needs).
+// directions run concurrently in the same launch (blockIdx.z).  CTAs that share a (direction,
+// utterance partition) synchronise once per time step through a monotonically increasing counter
+// in global memory (cooperative launch guarantees co-residency); the hidden state itself is
+// exchanged through the output array in L2 (ld.global.cg), which has to be written anyway.
 //
 // Data layout: time-major [T][B][H] fp32, so one time step of all utterances is contiguous.
 #include "common.cuh"
-#include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace ctcb {
 
@@ -41,38 +42,20 @@ struct SweepArgs {
     const float *act[2];    // mode 1: For, Back (for the within(0,maxAct) masks)
     float maxAct;
     int parts;              // utterance partitions (gridDim.y)
-    unsigned int *counters; // [0]: sticky poll-timeout flag, zeroed before launch
+    unsigned int *counters; // [2 * parts], zeroed before launch
 };
 
-constexpr unsigned SENTINEL = 0xffffffffu;
-constexpr long long POLL_CYCLES = 1000000000LL;   // ~0.5 s of polling: a lost producer becomes an error flag, not a hang
-
-__device__ __forceinline__ float4 ld_relaxed4(const float *p) {
-    float4 v;
-    asm volatile("ld.relaxed.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-// Re-polls must be ACQUIRE loads: a relaxed gpu-scope load can keep hitting the SM's stale L1 copy of
-// a line it fetched while the producer was still writing it (measured on B200: the poll never sees the
-// update); the acquire's CCTL.IVALL drops that copy.  A stale copy only ever holds sentinel-or-final
-// words, so a word that does not read as the sentinel is always the final value.
-__device__ __forceinline__ float4 ld_volatile4(const float *p) {
-    float4 v;
-    asm volatile("ld.acquire.gpu.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ float ld_volatile1(const float *p) {
-    float v;
-    asm volatile("ld.acquire.gpu.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
-    return v;
-}
-// Strong (gpu-scope, relaxed) store: a weak st.global may linger in the SM and race with the polls.
-__device__ __forceinline__ void st_relaxed_gpu(float *p, float v) {
-    asm volatile("st.relaxed.gpu.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-__device__ __forceinline__ bool is_sentinel(float x) { return __float_as_uint(x) == SENTINEL; }
-__device__ __forceinline__ bool any_sentinel(const float4 &v) {
-    return is_sentinel(v.x) || is_sentinel(v.y) || is_sentinel(v.z) || is_sentinel(v.w);
+__device__ __forceinline__ void domain_barrier(unsigned int *ctr, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(ctr, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
 }
 
 // KI > 0: H == 32*KI and the weights live in registers.  KI == 0: any H, weights re-read through L1/L2.
@@ -105,21 +88,12 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
     const int tiles_per_part = (ntiles + a.parts - 1) / a.parts;
     const int tile_beg = blockIdx.y * tiles_per_part;
     const int tile_end = min(ntiles, tile_beg + tiles_per_part);
+    unsigned int *ctr = a.counters + (dir * a.parts + blockIdx.y);
+    const unsigned int nslices = gridDim.x;
 
     // lane -> (row r, utterance b) of the value it ends up owning after the transposing reduction
     const int orow = lane >> 3, ob = lane & 7;
     const int oj = j0 + orow;
-
-    // Sentinel pre-fill by the producers themselves: every lane marks the words it will produce later
-    // as "not produced yet", then ONE grid-wide barrier (the only one of the sweep) orders all fills
-    // before any poll.  Same-thread program order then guarantees fill-before-produce.
-    for (int tile = tile_beg; tile < tile_end; ++tile) {
-        const int b = tile * SW_NB + ob;
-        if (oj < H && b < B)
-            for (int t = 0; t < T; ++t) st_relaxed_gpu(out + ((int64_t)t * B + b) * H + oj, __uint_as_float(SENTINEL));
-    }
-    __threadfence();
-    cooperative_groups::this_grid().sync();
 
     for (int s = 0; s < T; ++s) {
         const int t = ascending ? s : T - 1 - s;
@@ -144,67 +118,17 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                 // previous state of this tile's utterances: [SW_NB][H] from L2 -> shared
                 const float *src = out + ((int64_t)tprev * B + b0) * H;
                 const int nb = min(SW_NB, B - b0);
-                if (KI >= 4) {
-                    // all operand loads in flight at once, then re-poll only the words still unwritten
-                    constexpr int NCH = (KI >= 4) ? KI / 4 : 1;     // float4 chunks per thread: 8*H/4/256
+                if ((H & 3) == 0) {
                     const int h4 = H >> 2;
-                    float4 v[NCH];
-                    const float *p[NCH];
-                    bool need[NCH];
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        const int idx = threadIdx.x + c * SW_THREADS;
+                    for (int idx = threadIdx.x; idx < nb * h4; idx += SW_THREADS) {
                         const int bb = idx / h4, k4 = idx - bb * h4;
-                        need[c] = bb < nb;
-                        p[c] = src + (int64_t)bb * H + 4 * k4;
-                        v[c] = need[c] ? ld_relaxed4(p[c]) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                    int spins = 0;
-                    bool dead = false;
-                    long long t_start = 0;
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        while (need[c] && !dead && any_sentinel(v[c])) {   // producer has not stored this word yet
-                            if (spins == 0) t_start = clock64();
-                            if (((++spins & 63) == 0) &&
-                                (clock64() - t_start > POLL_CYCLES || *(volatile unsigned int *)a.counters != 0u)) {
-                                if (atomicCAS(a.counters, 0u, 1u) == 0u) {   // first timeout: who waited for what
-                                    a.counters[3] = (unsigned)s; a.counters[4] = blockIdx.x; a.counters[5] = blockIdx.y;
-                                    a.counters[6] = blockIdx.z; a.counters[7] = (unsigned)c; a.counters[8] = threadIdx.x;
-                                    a.counters[9] = (unsigned)tprev;
-                                }
-                                atomicAdd(a.counters + 2, 1u);
-                                if (threadIdx.x == 0 || a.counters[16 + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] == 0u)
-                                    a.counters[16 + (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = 1000u + (unsigned)s;
-                                dead = true;
-                                break;
-                            }
-                            v[c] = ld_volatile4(p[c]);
-                        }
-                    }
-#pragma unroll
-                    for (int c = 0; c < NCH; ++c) {
-                        const int idx = threadIdx.x + c * SW_THREADS;
-                        const int bb = idx / h4, k4 = idx - bb * h4;
-                        if (need[c]) *reinterpret_cast<float4 *>(hs + bb * Hp + 4 * k4) = v[c];
+                        const float4 v = __ldcg(reinterpret_cast<const float4 *>(src + (int64_t)bb * H) + k4);
+                        *reinterpret_cast<float4 *>(hs + bb * Hp + 4 * k4) = v;
                     }
                 } else {
                     for (int idx = threadIdx.x; idx < nb * H; idx += SW_THREADS) {
                         const int bb = idx / H, k = idx - bb * H;
-                        const float *p = src + (int64_t)bb * H + k;
-                        float v = ld_volatile1(p);
-                        int spins = 0;
-                        long long t_start = 0;
-                        while (is_sentinel(v)) {
-                            if (spins == 0) t_start = clock64();
-                            if (((++spins & 63) == 0) &&
-                                (clock64() - t_start > POLL_CYCLES || *(volatile unsigned int *)a.counters != 0u)) {
-                                atomicExch(a.counters, 1u);
-                                break;
-                            }
-                            v = ld_volatile1(p);
-                        }
-                        hs[bb * Hp + k] = v;
+                        hs[bb * Hp + k] = __ldcg(src + (int64_t)bb * H + k);
                     }
                 }
                 for (int idx = threadIdx.x + nb * Hp; idx < SW_NB * Hp; idx += SW_THREADS) hs[idx] = 0.f;
@@ -260,10 +184,10 @@ __global__ void __launch_bounds__(SW_THREADS, 1) sweep_kernel(SweepArgs a) {
                     v = (act_v > 0.f && act_v < a.maxAct) ? v : 0.f;   // within(0, maxAct)
                     if (t >= Tb) v = 0.f;
                 }
-                if (is_sentinel(v)) v = __uint_as_float(0x7fc00000u);   // a NaN result must not look unwritten
-                st_relaxed_gpu(out + ((int64_t)t * B + b) * H + oj, v);
+                out[((int64_t)t * B + b) * H + oj] = v;
             }
         }
+        if (s + 1 < T) domain_barrier(ctr, nslices * (unsigned int)(s + 1));
     }
 }
 
@@ -285,9 +209,11 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     const int ntiles = (a.B + SW_NB - 1) / SW_NB;
     int parts = capacity / (2 * slices);
     if (parts > ntiles) parts = ntiles;
+    if (parts > 500) parts = 500;   // counters region holds 1024 words
     if (parts < 1) parts = 1;
     a.parts = parts;
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * 1024, st));
+    a.counters += 16;     // words [0..15] are reserved for error flags
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters - 16, 0, sizeof(unsigned int) * (16 + 2 * parts), st));
     dim3 grid(slices, parts, 2);
     void *params[] = {&a};
     CTCB_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)sweep_kernel<KI>, grid, dim3(SW_THREADS), params, smem, st));
@@ -295,7 +221,11 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     return CTCB_OK;
 }
 
-// counters: >= 2*ceil(B/8) uint32 of device scratch
+int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
+                      const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
+                      unsigned int *err, cudaStream_t st, bool *handled);
+
+// counters: 4096 bytes of device scratch
 int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
               const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
               unsigned int *counters, cudaStream_t st) {
@@ -303,6 +233,20 @@ int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *p
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB;
     a.maxAct = maxAct; a.counters = counters; a.parts = 1;
+    {   // cluster/DSMEM fast path (H = 128, 256, 512); CTCB_SWEEP=barrier forces the general kernel
+        static int force_barrier = -1;
+        if (force_barrier < 0) {
+            const char *e = getenv("CTCB_SWEEP");
+            force_barrier = (e && e[0] == 'b') ? 1 : 0;
+        }
+        if (!force_barrier) {
+            bool handled = false;
+            CTCB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, st));
+            const int rc = run_sweep_cluster(mode, T, B, H, Tlen, pre, Wf, Wb, outF, outB, actF, actB, maxAct, counters, st, &handled);
+            if (rc != CTCB_OK) return rc;
+            if (handled) return CTCB_OK;
+        }
+    }
     const int slices = (H + SW_ROWS - 1) / SW_ROWS;
     const int Hp = (H + 3) / 4 * 4 + 4;
     const size_t smem = (size_t)SW_NB * Hp * sizeof(float);
