@@ -3,8 +3,8 @@
 // Same arithmetic as sweep.cu (reference loops brnnet.py:144-152 forward, :208-224 BPTT), but the
 // hidden state never touches global memory on the serial chain:
 //
-//   * one CLUSTER of CS = H/32 CTAs per (direction, tile of 8 utterances); CTA r owns 32 output units
-//     and keeps its 32 x H slice of the recurrent matrix in registers for the whole sweep;
+//   * one CLUSTER of CS CTAs per (direction, tile of NB utterances); CTA r owns ROWS output units
+//     (ROWS x NB = 256) and keeps its ROWS x H slice of the recurrent matrix in registers for the whole sweep;
 //   * every CTA holds the complete previous state of its 8 utterances in shared memory, laid out
 //     [slice][utterance][32] so that one CTA's contribution is one contiguous 1 KB block;
 //   * after a step, each CTA pushes its 1 KB block into the shared memory of all CS CTAs of the
@@ -13,11 +13,11 @@
 //     soon as the CS blocks of step s-1 have landed.  Two state buffers / two barriers alternate;
 //   * For/Back (dFor/dBack) are still streamed to HBM for the GEMMs that follow, off the chain.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace ctcb {
 
 constexpr int SC_THREADS = 256;
-constexpr int SC_NB = 8;
 
 struct SweepClusterArgs {
     int mode, T, B, H;
@@ -28,6 +28,7 @@ struct SweepClusterArgs {
     const float *act[2];
     float maxAct;
     unsigned int *err;      // [0] set to 2 if a barrier wait timed out (never a hang)
+    int opt;                // tuning bits (CTCB_SWEEP_OPT): 1 = one polling lane per warp, 2 = HBM store after the push
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -62,13 +63,19 @@ __device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta
                  ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
 }
 
-// KI = H/32 = cluster size.  grid = (KI, ntiles, 2), cluster = (KI, 1, 1).
-template <int KI>
+// KI = H/32.  RPW = output units per warp (4 or 8); a CTA owns ROWS = 8*RPW units of NB = 32/RPW
+// utterances, so its block is always 1 KB and the cluster has CS = H/ROWS CTAs.  Fewer, fatter CTAs
+// (RPW = 8) halve both the number of pushes and the shared-memory traffic per step; the price is
+// 8*KI weight registers per lane.  grid = (CS, ntiles, 2), cluster = (CS, 1, 1).
+template <int KI, int RPW>
 __global__ void __launch_bounds__(SC_THREADS, 1) sweep_cluster_kernel(SweepClusterArgs a) {
     constexpr int H = 32 * KI;
-    constexpr uint32_t BLK_BYTES = SC_NB * 32 * sizeof(float);          // one CTA's block: 1 KB
-    __shared__ __align__(128) float hbuf[2][KI * SC_NB * 32];           // [buffer][slice][utterance][32]
-    __shared__ __align__(128) float stage[2][SC_NB * 32];               // this CTA's new outputs [utterance][32]
+    constexpr int SC_NB = 32 / RPW;
+    constexpr int ROWS = 8 * RPW;
+    constexpr int CS = H / ROWS;
+    constexpr uint32_t BLK_BYTES = SC_NB * ROWS * sizeof(float);         // one CTA's block: 1 KB
+    __shared__ __align__(128) float hbuf[2][CS * SC_NB * ROWS];          // [buffer][slice][utterance][ROWS]
+    __shared__ __align__(128) float stage[2][SC_NB * ROWS];              // this CTA's new outputs [utterance][ROWS]
     __shared__ __align__(8) unsigned long long mbar[2];
 
     const int B = a.B, T = a.T;
@@ -81,11 +88,11 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sweep_cluster_kernel(SweepClust
     const float *act = a.act[dir];
     const bool bptt = (a.mode == 1);
     const bool ascending = (dir == 0) != bptt;
-    const int j0 = rank * 32 + warp * 4;
+    const int j0 = rank * ROWS + warp * RPW;
 
-    float wreg[4][KI];
+    float wreg[RPW][KI];
 #pragma unroll
-    for (int r = 0; r < 4; ++r)
+    for (int r = 0; r < RPW; ++r)
 #pragma unroll
         for (int i = 0; i < KI; ++i) {
             const int j = j0 + r, k = lane + 32 * i;
@@ -98,16 +105,17 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sweep_cluster_kernel(SweepClust
         mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         // arm both barriers for their first use (CS blocks of 1 KB each)
-        mbar_arrive_expect_tx(bar0, KI * BLK_BYTES);
-        mbar_arrive_expect_tx(bar1, KI * BLK_BYTES);
+        mbar_arrive_expect_tx(bar0, CS * BLK_BYTES);
+        mbar_arrive_expect_tx(bar1, CS * BLK_BYTES);
     }
     cluster_sync_all();      // barriers initialised cluster-wide before any peer pushes into them
 
-    const int orow = lane >> 3, ob = lane & 7;
+    const int orow = lane / SC_NB, ob = lane % SC_NB;
     const int oj = j0 + orow, b = b0 + ob;
     const bool valid = (b < B);
     const int Tb = valid ? __ldg(a.Tlen + b) : 0;
 
+    bool dead = false;
     for (int s = 0; s < T; ++s) {
         const int t = ascending ? s : T - 1 - s;
         float pre_v = 0.f, act_v = 0.f;
@@ -123,34 +131,40 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sweep_cluster_kernel(SweepClust
             // wait for the CS blocks of step s-1 (barrier s&1, use number (s-1)>>1)
             const uint32_t bar = (s & 1) ? bar1 : bar0;
             const uint32_t parity = (uint32_t)(((s - 1) >> 1) & 1);
-            if (!mbar_try_wait(bar, parity)) {
+            if ((lane == 0 || !(a.opt & 1)) && !dead && !mbar_try_wait(bar, parity)) {
                 const long long t_start = clock64();
-                bool dead = false;
                 while (!mbar_try_wait(bar, parity)) {
-                    if (clock64() - t_start > 1000000000LL) { dead = true; break; }   // ~0.5 s
+                    if (clock64() - t_start > 1000000000LL) {   // ~0.5 s: report, then run on without waiting
+                        dead = true;
+                        atomicExch(a.err, 2u);
+                        break;
+                    }
                 }
-                if (dead) { atomicExch(a.err, 2u); break; }
             }
+            __syncwarp();
             const float *hs = hbuf[s & 1];
 #pragma unroll
             for (int i = 0; i < KI; ++i) {
                 float hv[SC_NB];
 #pragma unroll
-                for (int bb = 0; bb < SC_NB; ++bb) hv[bb] = hs[(i * SC_NB + bb) * 32 + lane];
+                for (int bb = 0; bb < SC_NB; ++bb)
+                    hv[bb] = hs[((32 * i) / ROWS * SC_NB + bb) * ROWS + (32 * i) % ROWS + lane];
 #pragma unroll
-                for (int r = 0; r < 4; ++r)
+                for (int r = 0; r < RPW; ++r)
 #pragma unroll
-                    for (int bb = 0; bb < SC_NB; ++bb) acc[r * 8 + bb] = fmaf(wreg[r][i], hv[bb], acc[r * 8 + bb]);
+                    for (int bb = 0; bb < SC_NB; ++bb)
+                        acc[r * SC_NB + bb] = fmaf(wreg[r][i], hv[bb], acc[r * SC_NB + bb]);
             }
+        }
+        // transposing butterfly (unconditional: no collective inside a branch): lane l ends with acc[l] summed
 #pragma unroll
-            for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
-                const bool up = (lane & off) != 0;
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+            const bool up = (lane & off) != 0;
 #pragma unroll
-                for (int i = 0; i < n / 2; ++i) {
-                    const float send = up ? acc[i] : acc[i + n / 2];
-                    const float keep = up ? acc[i + n / 2] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
+            for (int i = 0; i < n / 2; ++i) {
+                const float send = up ? acc[i] : acc[i + n / 2];
+                const float keep = up ? acc[i + n / 2] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
             }
         }
         float v = 0.f;
@@ -159,53 +173,60 @@ __global__ void __launch_bounds__(SC_THREADS, 1) sweep_cluster_kernel(SweepClust
             if (!bptt) v = fminf(fmaxf(v, 0.f), a.maxAct);                     // minmax(0, maxAct)
             else v = (act_v > 0.f && act_v < a.maxAct) ? v : 0.f;              // within(0, maxAct)
             if (t >= Tb) v = 0.f;
-            out[((int64_t)t * B + b) * H + oj] = v;
+            if (!(a.opt & 2)) out[((int64_t)t * B + b) * H + oj] = v;
         }
         if (s + 1 < T) {
-            stage[s & 1][ob * 32 + warp * 4 + orow] = v;
+            stage[s & 1][ob * ROWS + warp * RPW + orow] = v;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic writes -> async proxy
             __syncthreads();   // block complete; every warp is done reading hbuf[s&1]
             if (warp == 0) {
                 if (s > 0 && lane == 0) {
                     // re-arm the barrier we just consumed for its next use (step s+2)
-                    mbar_arrive_expect_tx((s & 1) ? bar1 : bar0, KI * BLK_BYTES);
+                    mbar_arrive_expect_tx((s & 1) ? bar1 : bar0, CS * BLK_BYTES);
                 }
                 __syncwarp();
-                if (lane < KI) {
+                if (lane < CS) {
                     const int nb = (s + 1) & 1;
-                    const uint32_t dst = map_to_cta(smem_u32(&hbuf[nb][rank * SC_NB * 32]), (uint32_t)lane);
+                    const uint32_t dst = map_to_cta(smem_u32(&hbuf[nb][rank * SC_NB * ROWS]), (uint32_t)lane);
                     const uint32_t rbar = map_to_cta(nb ? bar1 : bar0, (uint32_t)lane);
                     bulk_push(dst, smem_u32(&stage[s & 1][0]), BLK_BYTES, rbar);
                 }
             }
         }
+        // stream the state to HBM for the GEMMs that follow -- after the push, so that the proxy fence
+        // of the exchange never waits for this store
+        if (valid && (a.opt & 2)) out[((int64_t)t * B + b) * H + oj] = v;
     }
     cluster_sync_all();      // no CTA may exit while peers can still address its shared memory
 }
 
-template <int KI>
-static int launch_cluster(const SweepClusterArgs &a, int ntiles, cudaStream_t st, bool *handled) {
+template <int KI, int RPW>
+static int launch_cluster(const SweepClusterArgs &a, cudaStream_t st, bool *handled) {
+    constexpr int CS = 4 * KI / RPW;
+    constexpr int NB = 32 / RPW;
+    const int ntiles = (a.B + NB - 1) / NB;
+    if (ntiles > 65535) return CTCB_OK;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(KI, ntiles, 2);
+    cfg.gridDim = dim3(CS, ntiles, 2);
     cfg.blockDim = dim3(SC_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = KI;
+    attr[0].val.clusterDim.x = CS;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    if (KI > 8)
-        CTCB_CUDA_CHECK(cudaFuncSetAttribute(sweep_cluster_kernel<KI>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    if (CS > 8)
+        CTCB_CUDA_CHECK(cudaFuncSetAttribute((sweep_cluster_kernel<KI, RPW>), cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, sweep_cluster_kernel<KI>, &cfg) != cudaSuccess || nclusters < 1) {
+    if (cudaOccupancyMaxActiveClusters(&nclusters, (sweep_cluster_kernel<KI, RPW>), &cfg) != cudaSuccess || nclusters < 1) {
         cudaGetLastError();
         *handled = false;     // this device/partition cannot host the cluster: use the general kernel
         return CTCB_OK;
     }
-    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_cluster_kernel<KI>, a));
+    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, (sweep_cluster_kernel<KI, RPW>), a));
     count_launch();
     *handled = true;
     return CTCB_OK;
@@ -219,12 +240,19 @@ int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const 
     SweepClusterArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB; a.maxAct = maxAct; a.err = err;
-    const int ntiles = (B + SC_NB - 1) / SC_NB;
-    if (ntiles > 65535) return CTCB_OK;
+    {
+        static int opt = -1;
+        if (opt < 0) { const char *e = getenv("CTCB_SWEEP_OPT"); opt = e ? atoi(e) : 0; }
+        a.opt = opt;
+    }
+    static int rpw_env = -1;   // CTCB_SWEEP_RPW=4|8 overrides the default shape
+    if (rpw_env < 0) { const char *e = getenv("CTCB_SWEEP_RPW"); rpw_env = e ? atoi(e) : 0; }
+    // defaults from measurements on B200 (tools/sweep_time.py): clusters of 8 CTAs are the sweet spot
+    const int rpw = rpw_env ? rpw_env : (H >= 256 ? 8 : 4);
     switch (H / 32) {
-        case 4: return launch_cluster<4>(a, ntiles, st, handled);
-        case 8: return launch_cluster<8>(a, ntiles, st, handled);
-        case 16: return launch_cluster<16>(a, ntiles, st, handled);
+        case 4: return launch_cluster<4, 4>(a, st, handled);
+        case 8: return rpw == 8 ? launch_cluster<8, 8>(a, st, handled) : launch_cluster<8, 4>(a, st, handled);
+        case 16: return rpw == 8 ? launch_cluster<16, 8>(a, st, handled) : launch_cluster<16, 4>(a, st, handled);
         default: return CTCB_OK;
     }
 }

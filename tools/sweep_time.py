@@ -1,0 +1,29 @@
+"""Time the two sweep launches of the C2 workload in isolation (forward + BPTT), events on the stream."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "stanford-ctc_b200")]
+import numpy as np, torch
+import _ctcb
+from _ctcb import lib, check, ptr
+T, B, H = [int(x) for x in (sys.argv[1:4] + ["200", "32", "512"][len(sys.argv) - 1:])]
+g = torch.Generator(device="cuda").manual_seed(1)
+s = 0.9 / np.sqrt(H / 3.0)
+Wf = (torch.rand(H, H, device="cuda", generator=g) * 2 - 1) * s
+Wb = (torch.rand(H, H, device="cuda", generator=g) * 2 - 1) * s
+pre = torch.randn(T, B, H, device="cuda", generator=g)
+lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
+oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty_like(oF); dF = torch.empty_like(oF); dB = torch.empty_like(oF)
+scr = torch.zeros(1024, dtype=torch.int32, device="cuda")
+st = _ctcb.current_stream()
+def fwd(): check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(oF), ptr(oB), None, None, 20.0, ptr(scr), st))
+def bwd(): check(lib.ctcb_brnn_sweep_f32(1, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(dF), ptr(dB), ptr(oF), ptr(oB), 20.0, ptr(scr), st))
+for _ in range(3): fwd(); bwd()
+torch.cuda.synchronize()
+for name, fn in (("fwd", fwd), ("bptt", bwd)):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20): fn()
+    e1.record(); torch.cuda.synchronize()
+    print("%s opt=%s sweep=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
+        name, os.environ.get("CTCB_SWEEP_OPT", "0"), os.environ.get("CTCB_SWEEP", "auto"), T, B, H,
+        e0.elapsed_time(e1) / 20, 1e3 * e0.elapsed_time(e1) / 20 / T, int(scr[0])))
