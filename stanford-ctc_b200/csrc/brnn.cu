@@ -181,12 +181,13 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
     w.ctc = take(ctcb_ctc_workspace_bytes(c->maxB, c->maxT, c->maxLabels));
     size_t g = 0;
     const int Rint = (int)((R > 0x7fffffff) ? 0x7fffffff : R);
+    auto need = [&](int M_, int N_, int K_) { size_t b = ctcb_gemm_workspace_bytes(M_, N_, K_); if (b > g) g = b; };
     for (int i = 0; i <= N; ++i) {
-        size_t b = ctcb_gemm_workspace_bytes(sizes[i + 1], sizes[i], Rint);
-        if (b > g) g = b;
+        need(Rint, sizes[i + 1], sizes[i]);      // forward   X_i . W^T
+        need(Rint, sizes[i], sizes[i + 1]);      // backward  delta . W
+        need(sizes[i + 1], sizes[i], Rint);      // weights   delta^T . X_i
     }
-    size_t b = ctcb_gemm_workspace_bytes(H, H, Rint);
-    if (b > g) g = b;
+    need(H, H, Rint);                            // recurrent weight gradients
     w.gemm = take(g);
     w.colsum = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
     w.scratch = take(8192);

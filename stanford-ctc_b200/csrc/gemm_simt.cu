@@ -220,11 +220,21 @@ static int choose_splits(int M, int N, int K) {
 
 }  // namespace ctcb
 
+namespace ctcb {
+bool gemm_tc_eligible(int M, int N, int K);
+size_t gemm_tc_workspace_bytes(int M, int N, int K);
+int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float *A, int64_t lda, const float *B,
+                int64_t ldb, float beta, float *C, int64_t ldc, const float *bias, int relu, const float *mask_src,
+                void *ws, size_t ws_bytes, cudaStream_t st);
+}
+
 using namespace ctcb;
 
 extern "C" size_t ctcb_gemm_workspace_bytes(int M, int N, int K) {
     const int s = choose_splits(M, N, K);
-    return s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+    size_t simt = s > 1 ? (size_t)s * M * N * sizeof(float) : 0;
+    size_t tc = gemm_tc_eligible(M, N, K) ? gemm_tc_workspace_bytes(M, N, K) : 0;
+    return simt > tc ? simt : tc;
 }
 
 extern "C" int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha, const float *A, int64_t lda,
@@ -232,6 +242,10 @@ extern "C" int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float 
                              int relu, const float *mask_src, void *workspace, size_t ws_bytes, void *stream) {
     if (M <= 0 || N <= 0) return CTCB_OK;
     if (!A || !B || !C || K < 0) return set_error(CTCB_EINVAL, "ctcb_gemm_f32: bad argument");
+    // large contractions: 3xTF32 on the tcgen05 tensor cores (gemm_tc.cu); small or odd ones: exact FFMA below
+    if (gemm_tc_eligible(M, N, K) && workspace && ws_bytes >= gemm_tc_workspace_bytes(M, N, K))
+        return run_gemm_tc(transA, transB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc, bias, relu, mask_src, workspace,
+                           ws_bytes, (cudaStream_t)stream);
     GemmArgs g;
     g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.alpha = alpha; g.beta = beta; g.bias = bias; g.relu = relu; g.mask = mask_src;

@@ -1,0 +1,424 @@
+// gemm_tc.cu -- fp32-faithful dense contraction on the 5th-generation tensor cores (tcgen05 + TMEM + TMA).
+//
+// The reference multiplies in float32 (cudamat cm.dot -> legacy cuBLAS sgemm; call sites
+// ctc_fast/nnets/brnnet.py:140,196,204,227-230).  tcgen05 has no fp32 MMA, and a single TF32 pass
+// (10-bit mantissa) would be a reduced-precision run, so every operand is split into two TF32 parts
+//     x = hi + lo,   hi = x with the low 13 mantissa bits cleared (what kind::tf32 reads from an fp32 word),
+//                    lo = x - hi (exact in fp32; itself read as TF32)
+// and a product is three MMAs accumulated in fp32 in tensor memory:  lo.hi + hi.lo + hi.hi
+// (the dropped lo.lo term is ~2^-20 relative) -- "3xTF32", ~1e-6 relative error per product.
+//
+// Kernel shape: C[M x N] = A[M x K] . B[N x K]^T, both operands K-major.  One CTA (4 warps) per
+// 128 x BN output tile and K split (gridDim.z):
+//   warp 0 / lane 0 : TMA producer -- per k-block of 32 floats four 128B-swizzled tiles
+//                     (A, A_lo, B, B_lo) into a STAGES-deep shared-memory ring, mbarrier complete_tx;
+//   warp 1 / lane 0 : MMA issuer  -- 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per k-block,
+//                     tcgen05.commit releases the ring slot; the last commit signals the epilogue;
+//   warps 0..3      : epilogue -- tcgen05.ld 32 lanes x 32 columns per warp, fused alpha/beta/bias/ReLU/
+//                     mask (or split-K partial), row stores.
+// Transposed operands and operands whose row pitch is not a multiple of 16 bytes are re-laid-out by the
+// prep kernel that also produces the lo parts, so the tensor-core kernel only ever sees K-major tiles.
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace ctcb {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;   // 32 fp32 = 128 bytes = one swizzle span
+
+struct GemmTcArgs {
+    int M, N, K;
+    float *C; int64_t ldc;
+    float alpha, beta;
+    const float *bias; int relu; const float *mask;
+    float *partial;      // split-K partials [splits][M][N] or nullptr
+    int kb_per_split;    // k-blocks per gridDim.z slice
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void tc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void tc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool tc_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol bug becomes a trap (CUDA error), never a hung GPU
+__device__ __forceinline__ void tc_mbar_wait(uint32_t bar, uint32_t parity) {
+    if (tc_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!tc_mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
+}
+__device__ __forceinline__ void tc_tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major, SWIZZLE_128B: 8-row x 128-byte atoms 1024 bytes apart
+// (cute/arch/mma_sm100_desc.hpp SmemDescriptor: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+//  version=1 [46,48), layout_type=2 (SWIZZLE_128B) [61,64)).
+__device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;                  // LBO (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO
+    d |= (uint64_t)1 << 46;                  // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
+    return d;
+}
+// Instruction descriptor for kind::tf32 (InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
+// both K-major, N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t tc_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int m, int n) {
+    float v = g.alpha * acc;
+    if (g.beta != 0.f) v += g.beta * g.C[(int64_t)m * g.ldc + n];
+    if (g.bias) v += g.bias[n];
+    if (g.relu) v = fmaxf(v, 0.f);
+    if (g.mask) v = (g.mask[(int64_t)m * g.ldc + n] > 0.f) ? v : 0.f;
+    return v;
+}
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(128, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, GemmTcArgs g) {
+    constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
+    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    extern __shared__ __align__(1024) uint8_t tc_smem[];
+    // 1024-byte alignment is required by SWIZZLE_128B: align manually (dynamic smem base is only 16B-aligned by contract)
+    uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+    const int nkb_total = (g.K + TC_BK - 1) / TC_BK;
+    const int kb0 = blockIdx.z * g.kb_per_split;
+    const int kb1 = min(nkb_total, kb0 + g.kb_per_split);
+    const int nkb = kb1 - kb0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc_mbar_init(tc_smem_u32(&bars[s]), 1);
+            tc_mbar_init(tc_smem_u32(&bars[STAGES + s]), 1);
+        }
+        tc_mbar_init(tc_smem_u32(&bars[2 * STAGES]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (nkb > 0) {
+        if (warp == 0 && lane == 0) {
+            // ------------------------------------------------------------ TMA producer
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, use = i / STAGES;
+                if (use > 0) tc_mbar_wait(tc_smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
+                const uint32_t full = tc_smem_u32(&bars[s]);
+                tc_mbar_expect_tx(full, STAGE_BYTES);
+                uint8_t *st = base + s * STAGE_BYTES;
+                const int k = (kb0 + i) * TC_BK;
+                tc_tma_load_2d(tc_smem_u32(st), &tmA, full, k, m0);
+                tc_tma_load_2d(tc_smem_u32(st + A_BYTES), &tmAl, full, k, m0);
+                tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES), &tmB, full, k, n0);
+                tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES + B_BYTES), &tmBl, full, k, n0);
+            }
+        } else if (warp == 1 && lane == 0) {
+            // ------------------------------------------------------------ MMA issuer
+            constexpr uint32_t idesc = tc_idesc(TC_BM, BN);
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, use = i / STAGES;
+                tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));
+                tc_fence_after();
+                const uint32_t a = tc_smem_u32(base + s * STAGE_BYTES);
+                const uint64_t dA = tc_smem_desc(a), dAl = tc_smem_desc(a + A_BYTES);
+                const uint64_t dB = tc_smem_desc(a + 2 * A_BYTES), dBl = tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+                for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);   // 8 floats = 32 bytes along the swizzled row
+                    tc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                    tc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
+                    tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                }
+                tc_commit(tc_smem_u32(&bars[STAGES + s]));         // slot free once these MMAs have read it
+            }
+            tc_commit(tc_smem_u32(&bars[2 * STAGES]));             // accumulator complete
+        }
+        __syncwarp();
+        // ---------------------------------------------------------------- epilogue (all 4 warps)
+        tc_mbar_wait(tc_smem_u32(&bars[2 * STAGES]), 0);
+        tc_fence_after();
+    }
+    const int m = m0 + warp * 32 + lane;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        if (nkb > 0) {
+            const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr) : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (m < g.M) {
+            float *drow = g.partial ? g.partial + ((int64_t)blockIdx.z * g.M + m) * g.N + n0 + c
+                                    : g.C + (int64_t)m * g.ldc + n0 + c;
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                v[j] = g.partial ? __uint_as_float(r[j])
+                                 : ((n0 + c + j < g.N) ? tc_epilogue(g, __uint_as_float(r[j]), m, n0 + c + j) : 0.f);
+            if (n0 + c + 32 <= g.N && (((uintptr_t)drow) & 15) == 0) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(drow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (n0 + c + j < g.N) drow[j] = v[j];
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------- prep kernels
+// out_lo[r][c] = x - trunc_tf32(x); optionally out_hi = x re-pitched.  No transpose: rows x cols, ld -> ldo.
+__global__ void tc_split_kernel(const float *__restrict__ x, int64_t ld, int rows, int cols, float *__restrict__ hi,
+                                float *__restrict__ lo, int64_t ldo) {
+    const int64_t total = (int64_t)rows * ldo;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int r = (int)(idx / ldo), c = (int)(idx - (int64_t)r * ldo);
+        const float v = (c < cols) ? x[(int64_t)r * ld + c] : 0.f;
+        const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        if (hi) hi[idx] = v;
+        lo[idx] = v - h;
+    }
+}
+// transposing variant: x is rows x cols (ld); outputs are cols x rows (ldo >= rows), tiled through shared memory
+__global__ void tc_split_transpose_kernel(const float *__restrict__ x, int64_t ld, int rows, int cols,
+                                          float *__restrict__ hi, float *__restrict__ lo, int64_t ldo) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + threadIdx.x;
+        tile[i][threadIdx.x] = (r < rows && c < cols) ? x[(int64_t)r * ld + c] : 0.f;
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + threadIdx.x;     // output row = c, output col = r
+        if (c < cols && r < ldo) {
+            const float v = (r < rows) ? tile[threadIdx.x][i] : 0.f;
+            const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+            hi[(int64_t)c * ldo + r] = v;
+            lo[(int64_t)c * ldo + r] = v - h;
+        }
+    }
+}
+
+__global__ void tc_splitk_reduce_kernel(GemmTcArgs g, int splits) {
+    const int64_t total = (int64_t)g.M * g.N;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int z = 0; z < splits; ++z) s += g.partial[(int64_t)z * total + idx];
+        const int m = (int)(idx / g.N), n = (int)(idx % g.N);
+        g.C[(int64_t)m * g.ldc + n] = tc_epilogue(g, s, m, n);
+    }
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// rows x K fp32, K-major with pitch ld (elements); box = 32 floats x box_rows, 128B swizzle, OOB -> 0
+static int make_map(CUtensorMap *m, const float *ptr, int rows, int K, int64_t ld, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%d K=%d ld=%lld", (int)r, rows, K, (long long)ld);
+    return CTCB_OK;
+}
+
+static inline int64_t pad4(int64_t x) { return (x + 3) / 4 * 4; }
+
+static int tc_choose_splits(int M, int N, int K, int BN) {
+    const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+    const int sms = num_sms();
+    if (tiles >= sms || nkb < 16) return 1;
+    int splits = (sms + tiles - 1) / tiles;
+    if (splits > nkb / 8) splits = nkb / 8;
+    if (splits > 32) splits = 32;
+    return splits < 1 ? 1 : splits;
+}
+
+bool gemm_tc_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = getenv("CTCB_GEMM");
+        on = (e && e[0] == 's') ? 0 : 1;     // CTCB_GEMM=simt forces the FFMA kernel everywhere
+        if (on && !get_encode()) on = 0;
+    }
+    return on == 1;
+}
+
+// measured on B200 (tools/gemm_check.py): below these sizes the exact FFMA kernel is as fast or faster
+bool gemm_tc_eligible(int M, int N, int K) { return gemm_tc_enabled() && M >= 64 && N >= 32 && K >= 128; }
+
+size_t gemm_tc_workspace_bytes(int M, int N, int K) {
+    const int64_t Kp = pad4(K);
+    size_t prep = (size_t)2 * ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float);
+    const int BN = (N <= 64) ? 64 : 128;
+    const int splits = tc_choose_splits(M, N, K, BN);
+    size_t part = splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
+    return align_up(prep, 256) + align_up(part, 256) + 1024;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap &tA, const CUtensorMap &tAl, const CUtensorMap &tB, const CUtensorMap &tBl,
+                     const GemmTcArgs &g, int splits, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
+    CTCB_CUDA_CHECK(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((g.N + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, splits);
+    gemm_tc_kernel<BN, STAGES><<<grid, 128, smem, st>>>(tA, tAl, tB, tBl, g);
+    CTCB_LAUNCH_CHECK();
+    return CTCB_OK;
+}
+
+// Same contract as ctcb_gemm_f32; ws must hold gemm_tc_workspace_bytes(M, N, K).
+int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const float *A, int64_t lda, const float *B,
+                int64_t ldb, float beta, float *C, int64_t ldc, const float *bias, int relu, const float *mask_src,
+                void *ws, size_t ws_bytes, cudaStream_t st) {
+    if (ws_bytes < gemm_tc_workspace_bytes(M, N, K)) return set_error(CTCB_ENOMEM, "run_gemm_tc: workspace too small");
+    const int64_t Kp = pad4(K);
+    float *p = (float *)ws;
+    float *Ahi = p; p += (size_t)M * Kp;
+    float *Alo = p; p += (size_t)M * Kp;
+    float *Bhi = p; p += (size_t)N * Kp;
+    float *Blo = p; p += (size_t)N * Kp;
+    float *part = (float *)((char *)ws + align_up((size_t)2 * ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float), 256));
+
+    // ---- operand A as M x K, K-major: stored M x K (transA=0) or K x M (transA=1)
+    const float *Ause; int64_t lda_use;
+    auto ew_grid = [](int64_t n) { int64_t b = (n + 255) / 256; const int cap = 16 * num_sms(); return (int)(b > cap ? cap : (b < 1 ? 1 : b)); };
+    if (transA) {
+        tc_split_transpose_kernel<<<dim3((M + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(A, lda, K, M, Ahi, Alo, Kp);
+        CTCB_LAUNCH_CHECK();
+        Ause = Ahi; lda_use = Kp;
+    } else {
+        const bool direct = (lda % 4 == 0) && (((uintptr_t)A) % 16 == 0);
+        tc_split_kernel<<<ew_grid((int64_t)M * Kp), 256, 0, st>>>(A, lda, M, K, direct ? nullptr : Ahi, Alo, Kp);
+        CTCB_LAUNCH_CHECK();
+        Ause = direct ? A : Ahi; lda_use = direct ? lda : Kp;
+    }
+    // ---- operand B as N x K, K-major: stored N x K (transB=1) or K x N (transB=0)
+    const float *Buse; int64_t ldb_use;
+    if (!transB) {
+        tc_split_transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Bhi, Blo, Kp);
+        CTCB_LAUNCH_CHECK();
+        Buse = Bhi; ldb_use = Kp;
+    } else {
+        const bool direct = (ldb % 4 == 0) && (((uintptr_t)B) % 16 == 0);
+        tc_split_kernel<<<ew_grid((int64_t)N * Kp), 256, 0, st>>>(B, ldb, N, K, direct ? nullptr : Bhi, Blo, Kp);
+        CTCB_LAUNCH_CHECK();
+        Buse = direct ? B : Bhi; ldb_use = direct ? ldb : Kp;
+    }
+
+    const int BN = (N <= 64) ? 64 : 128;
+    int splits = tc_choose_splits(M, N, K, BN);
+    const int nkb = (K + TC_BK - 1) / TC_BK;
+    GemmTcArgs g;
+    g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.bias = bias; g.relu = relu; g.mask = mask_src;
+    g.kb_per_split = (nkb + splits - 1) / splits;
+    splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
+    g.partial = splits > 1 ? part : nullptr;
+
+    CUtensorMap tA, tAl, tB, tBl;
+    int rc;
+    if ((rc = make_map(&tA, Ause, M, K, lda_use, TC_BM)) != CTCB_OK) return rc;
+    if ((rc = make_map(&tAl, Alo, M, K, Kp, TC_BM)) != CTCB_OK) return rc;
+    if ((rc = make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
+    if ((rc = make_map(&tBl, Blo, N, K, Kp, BN)) != CTCB_OK) return rc;
+    if (BN == 64) rc = launch_tc<64, 4>(tA, tAl, tB, tBl, g, splits, st);
+    else rc = launch_tc<128, 3>(tA, tAl, tB, tBl, g, splits, st);
+    if (rc != CTCB_OK) return rc;
+    if (splits > 1) {
+        const int64_t total = (int64_t)M * N;
+        int blocks = (int)((total + 255) / 256);
+        if (blocks > 4 * num_sms()) blocks = 4 * num_sms();
+        tc_splitk_reduce_kernel<<<blocks, 256, 0, st>>>(g, splits);
+        CTCB_LAUNCH_CHECK();
+    }
+    return CTCB_OK;
+}
+
+}  // namespace ctcb

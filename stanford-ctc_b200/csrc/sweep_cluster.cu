@@ -237,6 +237,11 @@ int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const 
                       unsigned int *err, cudaStream_t st, bool *handled) {
     *handled = false;
     if (H != 128 && H != 256 && H != 512) return CTCB_OK;
+    static int force_cluster = -1;   // CTCB_SWEEP=cluster takes this kernel for H = 512 too
+    if (force_cluster < 0) { const char *e = getenv("CTCB_SWEEP"); force_cluster = (e && e[0] == 'c') ? 1 : 0; }
+    // measured on B200 (tools/sweep_time.py, bench.py): clusters win 2x at H <= 256 (1.2 vs 2.6 us/step);
+    // at H = 512 the counter-barrier kernel is still ~5% ahead (3.2 vs 3.3 us/step), so it stays the default there
+    if (H == 512 && !force_cluster) return CTCB_OK;
     SweepClusterArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB; a.maxAct = maxAct; a.err = err;
