@@ -331,14 +331,17 @@ def run_ours(args, c):
     # ---------------------------------------------------------------- per-phase profile (untimed pass)
     roof = None
     phases = {}
+    # (every rank runs the pass -- the step contains the all-reduce -- but only rank 0 records events)
+    nprof = 10
     if rank == 0:
         lib.ctcb_profile_enable(1)
-        nprof = 10
-        for _ in range(nprof):
-            flush.zero_()
-            it += 1
-            opt.it = it
-            opt.step_device(batch, opt._momentum_now())
+    for _ in range(nprof):
+        flush.zero_()
+        it += 1
+        opt.it = it
+        opt.step_device(batch, opt._momentum_now())
+    barrier()
+    if rank == 0:
         import ctypes
         buf = ctypes.create_string_buffer(1 << 16)
         _ctcb.check(lib.ctcb_profile_report(buf, len(buf)))
