@@ -32,7 +32,7 @@ struct CtcArgs {
     int is_prob;
     int64_t us, fs;
     const int32_t *labels, *loff, *Tlen;
-    int B, Tmax, K, Kp, blank;
+    int B, Tmax, K, Kp, blank, vec2;
     float *grad, *nll;
     int32_t *skip;
     float *ws;            // alpha-tilde spill: [B][Tmax][Lpad] doubles
@@ -43,6 +43,10 @@ struct CtcArgs {
 __device__ __forceinline__ void cp_async4(float *dst, const float *src) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(float *dst, const float *src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -57,7 +61,11 @@ __device__ __forceinline__ void issue_tile(const CtcArgs &a, const float *base, 
         float *drow = te + r * Kp;
         if (t < T) {
             const float *row = base + (int64_t)t * a.fs;
-            for (int k = lane; k < K; k += 32) cp_async4(drow + k, row + k);
+            if (a.vec2) {        // rows and the padded shared rows are 8-byte aligned: half the copies
+                for (int k = 2 * lane; k < K; k += 64) cp_async8(drow + k, row + k);
+            } else {
+                for (int k = lane; k < K; k += 32) cp_async4(drow + k, row + k);
+            }
         } else {
             for (int k = lane; k < K; k += 32) drow[k] = 0.f;
         }
@@ -78,7 +86,7 @@ __device__ __forceinline__ float tile_stats(const CtcArgs &a, int t0, int T, flo
         m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
         float z = 0.f;
         for (int k = h; k < K; k += 2) {
-            const float e = expf(row[k] - m);
+            const float e = __expf(row[k] - m);
             row[k] = e;
             z += e;
         }
@@ -142,6 +150,9 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         double ab[P], al[P];
 #pragma unroll
         for (int j = 0; j < P; ++j) ab[j] = al[j] = 0.0;
+        // virtual state before frame 0: a unit mass on the first blank makes frame 0 an ordinary frame
+        // (alpha[0,0] = p_blank, alpha[1,0] = p_label0, ctc_fast.pyx:42-47) -- no special case in the loop
+        if (lane == 0) ab[0] = 1.0;
         int kscale = 0;   // power of two applied to the next frame
         issue_tile(a, base, 0, T, te0, lane);
         for (int tile = 0; tile < ntiles && !fail; ++tile) {
@@ -162,7 +173,7 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
                 const float *row = te + r * Kp;
                 const double eb = (double)row[blank];
                 int start = 2 * (T - t);
-                start = (t == 0 || L <= start) ? 0 : L - start;
+                start = (L <= start) ? 0 : L - start;
                 double pl = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
                 if (lane == 0) pl = 0.0;
                 const double sc = pow2_from_field(1023 + kscale);
@@ -173,12 +184,11 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
                     const double el = (lab[j] >= 0) ? (double)row[lab[j]] : 0.0;
                     double b = (ab[j] + pl) * eb;
                     double l = (al[j] + ab[j] + (allow_a[j] ? pl : 0.0)) * el;
-                    if (t == 0) {                       // :42-47
-                        b = (i == 0) ? eb : 0.0;
-                        l = (i == 0) ? el : 0.0;
+                    if (i > nlab) b = 0.0;
+                    if (start > 0) {                    // warp-uniform: only the last |l| frames prune
+                        if (2 * i < start) b = 0.0;
+                        if (2 * i + 1 < start) l = 0.0;
                     }
-                    if (2 * i < start || i > nlab) b = 0.0;
-                    if (2 * i + 1 < start) l = 0.0;
                     pl = al[j];
                     ab[j] = b * sc;
                     al[j] = l * sc;
@@ -215,6 +225,11 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         double bb[P], bl[P];
 #pragma unroll
         for (int j = 0; j < P; ++j) bb[j] = bl[j] = 0.0;
+        // virtual state after the last frame: unit mass "beyond" the final blank, so that frame T-1 gets
+        // pre[L-1] = pre[L-2] = 1 (ctc_fast.pyx:78-83) from the ordinary recurrence
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            if (lane * P + j == nlab) bb[j] = 1.0;
         int kscale = 0;
         issue_tile(a, base, (ntiles - 1) * TT, T, te0 + ((ntiles - 1) & 1) * TT * Kp, lane);
         for (int tile = ntiles - 1; tile >= 0 && !fail; --tile) {
@@ -254,7 +269,7 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
 #pragma unroll
                         for (int j = 0; j < P; ++j) an[j] = arow[j];
                     }
-                    const int end = (t == T - 1) ? L : min(2 * t + 2, L);
+                    const int end = min(2 * t + 2, L);
                     double nxb = __shfl_down_sync(0xffffffffu, bb[0], 1);
                     double nxl = __shfl_down_sync(0xffffffffu, bl[0], 1);
                     if (lane == 31) nxb = nxl = 0.0;
@@ -269,12 +284,12 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
                         // pre-emission sums: beta[s,t] = pre[s] * p[lab(s),t]
                         double pb = bb[j] + bl[j];
                         double pll = bl[j] + b1 + (allow_b[j] ? l1 : 0.0);
-                        if (t == T - 1) {               // :78-83
-                            pb = (i == nlab) ? 1.0 : 0.0;
-                            pll = (i == nlab - 1) ? 1.0 : 0.0;
+                        if (i > nlab) pb = 0.0;
+                        if (lab[j] < 0) pll = 0.0;
+                        if (end < L) {                  // warp-uniform: only the first |l| frames prune
+                            if (2 * i >= end) pb = 0.0;
+                            if (2 * i + 1 >= end) pll = 0.0;
                         }
-                        if (2 * i >= end || i > nlab) pb = 0.0;
-                        if (2 * i + 1 >= end || lab[j] < 0) pll = 0.0;
                         pb *= sc;
                         pll *= sc;
                         // occupancy numerators alpha*beta/p = alpha * pre  (no division by p, :117-136)
@@ -291,20 +306,25 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
                     for (int j = 0; j < P; ++j) bb[j] = nb[j];
                     const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
                     kscale = 1023 - emax;
-                    // absum and the blank occupancy: one interleaved butterfly (off the recurrence chain)
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        w += __shfl_xor_sync(0xffffffffu, w, o);
-                        wb += __shfl_xor_sync(0xffffffffu, wb, o);
-                    }
-                    if (emax == 0 || !(w > 0.0)) { fail = true; break; }
-                    const double winv = 1.0 / w;
+                    if (emax == 0) { fail = true; break; }        // beta mass gone: ZeroDivisionError in :109-114
+                    // absum (sum of all numerators) and the blank occupancy without a float64 butterfly: scale the
+                    // lane sums by a common power of two (largest lane exponent, one REDUX.MAX), quantise to 2^-24 of
+                    // it and add with the integer REDUX.ADD.  alpha*beta can underflow float64 for every state of a
+                    // frame (thousands of uninformative frames); the reference then leaves the frame at grad = p
+                    // (absum == 0 -> :141-145, no skip), which is what wsum == 0 does here.
+                    const int ew = __reduce_max_sync(0xffffffffu, dexp_field(w));
+                    const double wscale = (ew >= 24) ? pow2_from_field(2070 - ew) : 0.0;   // largest lane sum -> [2^24, 2^25)
+                    const unsigned wq = (unsigned)__double2uint_rz(w * wscale);
+                    const unsigned wbq = (unsigned)__double2uint_rz(wb * wscale);
+                    const unsigned wsum = __reduce_add_sync(0xffffffffu, wq);
+                    const unsigned wbsum = __reduce_add_sync(0xffffffffu, wbq);
+                    const float winv = (wsum > 0u) ? 1.f / (float)wsum : 0.f;
 #pragma unroll
                     for (int j = 0; j < P; ++j) {
-                        const float g = (float)(nl[j] * winv);
+                        const float g = (float)(nl[j] * wscale) * winv;
                         if (g > 0.f) atomicAdd(grow + lab[j], (unsigned)(g * GFIX + 0.5f));
                     }
-                    if (lane == 0) atomicAdd(grow + blank, (unsigned)((float)(wb * winv) * GFIX + 0.5f));
+                    if (lane == 0) atomicAdd(grow + blank, (unsigned)((float)wbsum * winv * GFIX + 0.5f));
                 }
             }
             __syncwarp();
@@ -417,7 +437,12 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     CtcArgs a;
     a.acts = acts; a.is_prob = is_prob; a.us = utt_stride; a.fs = frame_stride;
     a.labels = labels; a.loff = label_off; a.Tlen = T_per_utt;
-    a.B = B; a.Tmax = Tmax; a.K = K; a.Kp = K | 1; a.blank = blank;
+    a.B = B; a.Tmax = Tmax; a.K = K; a.blank = blank;
+    // 8-byte copies need even K, even strides, an 8-byte aligned base and an even shared row pitch
+    a.vec2 = (K % 2 == 0) && (utt_stride % 2 == 0) && (frame_stride % 2 == 0) && (((uintptr_t)acts) % 8 == 0);
+    // shared row pitch: odd (4-byte copies) or = 2 mod 32 (8-byte copies) so that the 16 rows of a tile start in
+    // different banks for the per-row statistics pass
+    a.Kp = a.vec2 ? ((K + 29) / 32 * 32 + 2) : (K | 1);
     a.grad = grad_out; a.nll = nll_out; a.skip = skip_out;
     a.ws = (float *)workspace; a.ws_utt = (int64_t)Tmax * 64 * P;
 
