@@ -230,6 +230,17 @@ class ClockSampler(object):
         return out
 
 
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch of a kernel from the committed ncu --set full capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic_r1.json")
+    if not os.path.exists(p):
+        return None
+    for k, v in json.load(open(p)).items():
+        if k.startswith(kernel_prefix):
+            return v
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -358,7 +369,8 @@ def run_ours(args, c):
         ach = fl / (launch_ms * 1e-3) / 1e12
         roof = {"kernel": "sweep_kernel (recurrent forward/BPTT sweeps, 2 launches/step)", "bound": "tensor",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": None, "peak_source": pk["src"] + " bf16 sustained",
+                "traffic": ncu_traffic("sweep_kernel") if (c["H"] == 512 and Bl == 32) else None,
+                "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": sweep_ms / tot if tot else None, "dominant_phase": dom,
                 "note": "exact-fp32 FFMA recurrence, serial in t: bounded by per-step barrier latency, not by the tensor pipe"}
 
@@ -390,7 +402,8 @@ def run_ours(args, c):
         pk = peaks()
         roof_ctc = {"kernel": "ctc_warp_kernel (isolation, B=%d x C1 shape, %.0f MB > L2)" % (Bc, alg / 1e6),
                     "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
-                    "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                    "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"],
+                    "traffic": ncu_traffic("ctc_warp_kernel") if (T == 200 and K == 62) else None,
                     "utterances_per_s": Bc / (ms * 1e-3), "ms": ms, "peak_source": pk["src"]}
         del acts, grad, ws
 
