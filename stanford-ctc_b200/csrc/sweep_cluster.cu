@@ -257,24 +257,26 @@ __device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long 
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
 }
 
-// HALVES = 1: one group of 4 utterances per cluster.  HALVES = 2: two groups that share the weight
-// registers and are processed back to back in every step, each with its own state buffers and mbarriers,
-// so the exchange of one group overlaps the arithmetic of the other (used when the grid would otherwise
-// need more clusters than the device can hold at once: 15 clusters of 8 on B200).
-template <int KI, int HALVES>
+// NB = utterances per cluster (4..8).  B200 holds at most 15 clusters of 8 CTAs at once, so the launcher picks
+// the smallest NB with 2*ceil(B/NB) <= that limit (B = 32 -> NB = 5, 14 clusters): a second wave of clusters
+// would double the time of the whole sweep.
+template <int KI, int NB>
 __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel_v3(SweepClusterArgs a) {
     constexpr int H = 32 * KI;
     constexpr int CS = H / 64;
-    constexpr int NB = 4;
-    constexpr uint32_t BLK_BYTES = 64 * NB * sizeof(float);              // 1 KB
-    __shared__ __align__(128) float hbuf[HALVES][2][CS * 256];
-    __shared__ __align__(128) float stage[HALVES][2][256];
-    __shared__ __align__(8) unsigned long long mbar[HALVES][2];
+    constexpr int NP = (NB + 1) / 2;                                     // utterance pairs
+    constexpr int NV = 4 * NB;                                           // outputs per warp (<= 32)
+    constexpr int BLKF = NP * 128;                                       // floats per CTA block
+    constexpr uint32_t BLK_BYTES = BLKF * sizeof(float);
+    __shared__ __align__(128) float hbuf[2][CS * BLKF];                  // [buffer][slice][utt pair][unit pair][4]
+    __shared__ __align__(128) float stage[2][BLKF];
+    __shared__ __align__(8) unsigned long long mbar[2];
 
     const int B = a.B, T = a.T;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;        // 16 warps
     const int rank = blockIdx.x;
     const int dir = blockIdx.z;
+    const int b0 = blockIdx.y * NB;
     const float *W = a.W[dir];
     float *out = a.out[dir];
     const float *act = a.act[dir];
@@ -291,119 +293,102 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel_v3(SweepClusterAr
             w2[r][ip] = bptt ? pack2(W[(int64_t)k * H + j], W[(int64_t)(k + 1) * H + j])
                              : pack2(W[(int64_t)j * H + k], W[(int64_t)j * H + k + 1]);
         }
+    // the padding utterance of an odd NB must read as zero in every buffer
+    for (int i = threadIdx.x; i < 2 * BLKF; i += 512) (&stage[0][0])[i] = 0.f;
 
+    const uint32_t bar0 = smem_u32(&mbar[0]), bar1 = smem_u32(&mbar[1]);
     if (threadIdx.x == 0) {
-#pragma unroll
-        for (int hf = 0; hf < HALVES; ++hf)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                mbar_init(smem_u32(&mbar[hf][q]), 1);
-            }
+        mbar_init(bar0, 1);
+        mbar_init(bar1, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-#pragma unroll
-        for (int hf = 0; hf < HALVES; ++hf)
-#pragma unroll
-            for (int q = 0; q < 2; ++q) mbar_arrive_expect_tx(smem_u32(&mbar[hf][q]), CS * BLK_BYTES);
+        mbar_arrive_expect_tx(bar0, CS * BLK_BYTES);
+        mbar_arrive_expect_tx(bar1, CS * BLK_BYTES);
     }
     cluster_sync_all();
 
-    // after the reduction lane l (and l^16) owns output index l & 15 = orow*4 + ob; lanes < 16 write it
-    const int oidx = lane & 15, orow = oidx >> 2, ob = oidx & 3;
-    const int oj = j0 + orow;
-    int bq[HALVES], Tbq[HALVES];
-    bool validq[HALVES];
-#pragma unroll
-    for (int hf = 0; hf < HALVES; ++hf) {
-        bq[hf] = (blockIdx.y * HALVES + hf) * NB + ob;
-        validq[hf] = (bq[hf] < B) && (lane < 16);
-        Tbq[hf] = (bq[hf] < B) ? __ldg(a.Tlen + bq[hf]) : 0;
-    }
+    // after the reduction lane l owns output index l = orow*NB + ob (lanes >= NV idle)
+    const int orow = lane / NB, ob = lane % NB;
+    const int oj = j0 + orow, b = b0 + ob;
+    const bool valid = (lane < NV) && (b < B);
+    const int Tb = valid ? __ldg(a.Tlen + b) : 0;
     bool dead = false;
 
     for (int s = 0; s < T; ++s) {
         const int t = ascending ? s : T - 1 - s;
+        float pre_v = 0.f, act_v = 0.f;
+        if (valid) {
+            const int64_t o = ((int64_t)t * B + b) * H + oj;
+            pre_v = __ldg(a.pre + o);
+            if (bptt) act_v = __ldg(act + o);
+        }
+        float acc[32];
 #pragma unroll
-        for (int hf = 0; hf < HALVES; ++hf) {
-            const int b = bq[hf];
-            const bool valid = validq[hf];
-            float pre_v = 0.f, act_v = 0.f;
-            if (valid) {
-                const int64_t o = ((int64_t)t * B + b) * H + oj;
-                pre_v = __ldg(a.pre + o);
-                if (bptt) act_v = __ldg(act + o);
-            }
-            float acc[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] = 0.f;
-            if (s > 0) {
-                const uint32_t bar = smem_u32(&mbar[hf][s & 1]);
-                const uint32_t parity = (uint32_t)(((s - 1) >> 1) & 1);
-                if (!dead && !mbar_try_wait(bar, parity)) {
-                    const long long t_start = clock64();
-                    while (!mbar_try_wait(bar, parity)) {
-                        if (clock64() - t_start > 1000000000LL) {   // ~0.5 s: report, then run on without waiting
-                            dead = true;
-                            atomicExch(a.err, 2u);
-                            break;
-                        }
+        for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+        if (s > 0) {
+            const uint32_t bar = (s & 1) ? bar1 : bar0;
+            const uint32_t parity = (uint32_t)(((s - 1) >> 1) & 1);
+            if (!dead && !mbar_try_wait(bar, parity)) {
+                const long long t_start = clock64();
+                while (!mbar_try_wait(bar, parity)) {
+                    if (clock64() - t_start > 1000000000LL) {   // ~0.5 s: report, then run on without waiting
+                        dead = true;
+                        atomicExch(a.err, 2u);
+                        break;
                     }
                 }
-                const ulonglong2 *hs = reinterpret_cast<const ulonglong2 *>(hbuf[hf][s & 1]);
-                unsigned long long acc2[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc2[i] = 0ull;
-#pragma unroll
-                for (int ip = 0; ip < CS; ++ip) {
-                    const ulonglong2 h01 = hs[ip * 64 + lane];          // {k,k+1} x utterances 0,1
-                    const ulonglong2 h23 = hs[ip * 64 + 32 + lane];     // {k,k+1} x utterances 2,3
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-                        ffma2(acc2[r * 4 + 0], w2[r][ip], h01.x);
-                        ffma2(acc2[r * 4 + 1], w2[r][ip], h01.y);
-                        ffma2(acc2[r * 4 + 2], w2[r][ip], h23.x);
-                        ffma2(acc2[r * 4 + 3], w2[r][ip], h23.y);
-                    }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) acc[i] = sum2(acc2[i]);
             }
-            // 16 values x 32 lanes -> lane l holds the full sum of value l & 15
+            const ulonglong2 *hs = reinterpret_cast<const ulonglong2 *>(hbuf[s & 1]);
+            unsigned long long acc2[NV];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+            for (int i = 0; i < NV; ++i) acc2[i] = 0ull;
 #pragma unroll
-            for (int off = 8, n = 16; off >= 1; off >>= 1, n >>= 1) {
-                const bool up = (lane & off) != 0;
+            for (int ip = 0; ip < CS; ++ip) {
+                ulonglong2 hv[NP];
 #pragma unroll
-                for (int i = 0; i < n / 2; ++i) {
-                    const float send = up ? acc[i] : acc[i + n / 2];
-                    const float keep = up ? acc[i + n / 2] : acc[i];
-                    acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-                }
+                for (int q = 0; q < NP; ++q) hv[q] = hs[ip * (BLKF / 4) + q * 32 + lane];   // {k,k+1} x utterances 2q,2q+1
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int u = 0; u < NB; ++u)
+                        ffma2(acc2[r * NB + u], w2[r][ip], (u & 1) ? hv[u >> 1].y : hv[u >> 1].x);
             }
-            float v = 0.f;
-            if (valid) {
-                v = pre_v + acc[0];
-                if (!bptt) v = fminf(fmaxf(v, 0.f), a.maxAct);
-                else v = (act_v > 0.f && act_v < a.maxAct) ? v : 0.f;
-                if (t >= Tbq[hf]) v = 0.f;
-                out[((int64_t)t * B + b) * H + oj] = v;
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] = sum2(acc2[i]);
+        }
+        // transposing butterfly over 32 slots (slots >= NV are zero): lane l ends with the full sum of slot l
+#pragma unroll
+        for (int off = 16, n = 32; off >= 1; off >>= 1, n >>= 1) {
+            const bool up = (lane & off) != 0;
+#pragma unroll
+            for (int i = 0; i < n / 2; ++i) {
+                const float send = up ? acc[i] : acc[i + n / 2];
+                const float keep = up ? acc[i + n / 2] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
             }
-            if (s + 1 < T) {
-                if (lane < 16) {
-                    const int jl = warp * 4 + orow;     // local unit 0..63
-                    stage[hf][s & 1][(ob >> 1) * 128 + (jl >> 1) * 4 + (ob & 1) * 2 + (jl & 1)] = v;
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                __syncthreads();
-                if (warp == 0) {
-                    if (s > 0 && lane == 0) mbar_arrive_expect_tx(smem_u32(&mbar[hf][s & 1]), CS * BLK_BYTES);
-                    __syncwarp();
-                    if (lane < CS) {
-                        const int nb = (s + 1) & 1;
-                        const uint32_t dst = map_to_cta(smem_u32(&hbuf[hf][nb][rank * 256]), (uint32_t)lane);
-                        const uint32_t rbar = map_to_cta(smem_u32(&mbar[hf][nb]), (uint32_t)lane);
-                        bulk_push(dst, smem_u32(&stage[hf][s & 1][0]), BLK_BYTES, rbar);
-                    }
+        }
+        float v = 0.f;
+        if (valid) {
+            v = pre_v + acc[0];
+            if (!bptt) v = fminf(fmaxf(v, 0.f), a.maxAct);
+            else v = (act_v > 0.f && act_v < a.maxAct) ? v : 0.f;
+            if (t >= Tb) v = 0.f;
+            out[((int64_t)t * B + b) * H + oj] = v;
+        }
+        if (s + 1 < T) {
+            if (lane < NV) {
+                const int jl = warp * 4 + orow;     // local unit 0..63
+                stage[s & 1][(ob >> 1) * 128 + (jl >> 1) * 4 + (ob & 1) * 2 + (jl & 1)] = v;
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            if (warp == 0) {
+                if (s > 0 && lane == 0) mbar_arrive_expect_tx((s & 1) ? bar1 : bar0, CS * BLK_BYTES);
+                __syncwarp();
+                if (lane < CS) {
+                    const int nb = (s + 1) & 1;
+                    const uint32_t dst = map_to_cta(smem_u32(&hbuf[nb][rank * BLKF]), (uint32_t)lane);
+                    const uint32_t rbar = map_to_cta(nb ? bar1 : bar0, (uint32_t)lane);
+                    bulk_push(dst, smem_u32(&stage[s & 1][0]), BLK_BYTES, rbar);
                 }
             }
         }
@@ -411,11 +396,9 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel_v3(SweepClusterAr
     cluster_sync_all();
 }
 
-template <int KI, int HALVES>
-static int launch_cluster_v3(const SweepClusterArgs &a, cudaStream_t st, bool *handled) {
+template <int KI, int NB>
+static int launch_cluster_v3_nb(const SweepClusterArgs &a, int ntiles, cudaStream_t st) {
     constexpr int CS = KI / 2;
-    const int ntiles = (a.B + 4 * HALVES - 1) / (4 * HALVES);
-    if (ntiles > 65535) return CTCB_OK;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(CS, ntiles, 2);
     cfg.blockDim = dim3(512);
@@ -428,25 +411,49 @@ static int launch_cluster_v3(const SweepClusterArgs &a, cudaStream_t st, bool *h
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    int nclusters = 0;
-    if (cudaOccupancyMaxActiveClusters(&nclusters, (sweep_cluster_kernel_v3<KI, HALVES>), &cfg) != cudaSuccess || nclusters < 1) {
-        cudaGetLastError();
-        *handled = false;
-        return CTCB_OK;
-    }
-    if (HALVES == 1 && ntiles * 2 > nclusters) {
-        // more clusters than the device holds at once would run in two waves: let every cluster carry two
-        // utterance groups instead (their exchange/compute phases interleave)
-        return launch_cluster_v3<KI, 2>(a, st, handled);
-    }
-    if (getenv("CTCB_DEBUG")) {
-        static bool once = false;
-        if (!once) { once = true; fprintf(stderr, "[ctcb] sweep v3 H=%d halves=%d: cluster=%d, grid clusters=%d, max active clusters=%d\n", 32 * KI, HALVES, CS, ntiles * 2, nclusters); }
-    }
-    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, (sweep_cluster_kernel_v3<KI, HALVES>), a));
+    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, (sweep_cluster_kernel_v3<KI, NB>), a));
     count_launch();
-    *handled = true;
     return CTCB_OK;
+}
+
+template <int KI>
+static int launch_cluster_v3(const SweepClusterArgs &a, cudaStream_t st, bool *handled) {
+    constexpr int CS = KI / 2;
+    // how many clusters of this shape the device holds at once (shape-independent of NB up to shared memory)
+    static int max_clusters = -1;
+    if (max_clusters < 0) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(CS, 64, 2);
+        cfg.blockDim = dim3(512);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, (sweep_cluster_kernel_v3<KI, 8>), &cfg) != cudaSuccess) { cudaGetLastError(); n = 0; }
+        max_clusters = n;
+        if (getenv("CTCB_DEBUG")) fprintf(stderr, "[ctcb] sweep v3 H=%d: cluster=%d CTAs, max active clusters=%d\n", 32 * KI, CS, n);
+    }
+    *handled = false;
+    if (max_clusters < 2) return CTCB_OK;
+    static int nb_env = -1;   // CTCB_SWEEP_NB=4..8 forces the group size
+    if (nb_env < 0) { const char *e = getenv("CTCB_SWEEP_NB"); nb_env = e ? atoi(e) : 0; }
+    int nb = 0;
+    for (int c = 4; c <= 8; ++c)
+        if (2 * ((a.B + c - 1) / c) <= max_clusters) { nb = c; break; }
+    if (nb_env >= 4 && nb_env <= 8) nb = nb_env;
+    if (nb == 0) return CTCB_OK;          // would need a second wave of clusters: the general kernel is faster
+    const int ntiles = (a.B + nb - 1) / nb;
+    int rc;
+    switch (nb) {
+        case 4: rc = launch_cluster_v3_nb<KI, 4>(a, ntiles, st); break;
+        case 5: rc = launch_cluster_v3_nb<KI, 5>(a, ntiles, st); break;
+        case 6: rc = launch_cluster_v3_nb<KI, 6>(a, ntiles, st); break;
+        case 7: rc = launch_cluster_v3_nb<KI, 7>(a, ntiles, st); break;
+        default: rc = launch_cluster_v3_nb<KI, 8>(a, ntiles, st); break;
+    }
+    if (rc == CTCB_OK) *handled = true;
+    return rc;
 }
 
 int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
@@ -456,9 +463,7 @@ int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const 
     if (H != 128 && H != 256 && H != 512) return CTCB_OK;
     static int force_cluster = -1;   // CTCB_SWEEP=cluster takes this kernel for H = 512 too
     if (force_cluster < 0) { const char *e = getenv("CTCB_SWEEP"); force_cluster = (e && e[0] == 'c') ? 1 : 0; }
-    // measured on B200 (tools/sweep_time.py, bench.py): clusters win 2x at H <= 256 (1.2 vs 2.6 us/step);
-    // at H = 512 the counter-barrier kernel is still ~5% ahead (3.2 vs 3.3 us/step), so it stays the default there
-    if (H == 512 && !force_cluster) return CTCB_OK;
+    (void)force_cluster;
     SweepClusterArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB; a.maxAct = maxAct; a.err = err;
@@ -468,12 +473,13 @@ int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const 
         a.opt = opt;
     }
     static int ver_env = -1;   // CTCB_SWEEP_V=2 selects the 8-warp kernels below instead of v3
-    if (ver_env < 0) { const char *e = getenv("CTCB_SWEEP_V"); ver_env = e ? atoi(e) : 3; }
-    if (ver_env == 3) {
+    if (ver_env < 0) { const char *e = getenv("CTCB_SWEEP_V"); ver_env = e ? atoi(e) : 0; }
+    // measured (tools/sweep_time.py, B=32, T=200): H=512 v3 0.46 ms vs v2 0.69 vs barrier 0.63; H=256 v2 0.23 vs v3 0.27
+    if (ver_env == 3 || (ver_env == 0 && H == 512)) {
         switch (H / 32) {
-            case 4: return launch_cluster_v3<4, 1>(a, st, handled);
-            case 8: return launch_cluster_v3<8, 1>(a, st, handled);
-            case 16: return launch_cluster_v3<16, 1>(a, st, handled);
+            case 4: return launch_cluster_v3<4>(a, st, handled);
+            case 8: return launch_cluster_v3<8>(a, st, handled);
+            case 16: return launch_cluster_v3<16>(a, st, handled);
             default: return CTCB_OK;
         }
     }
