@@ -101,6 +101,10 @@ int64_t ctcb_brnn_param_count(const ctcb_brnn_config *cfg);
 int ctcb_brnn_num_tensors(const ctcb_brnn_config *cfg);                    /* 2 * len(stack) */
 int ctcb_brnn_tensor_info(const ctcb_brnn_config *cfg, int idx, int64_t *offset, int32_t *rows, int32_t *cols);
 size_t ctcb_brnn_workspace_bytes(const ctcb_brnn_config *cfg);
+/* Byte offset, inside the workspace, of a uint32 that the recurrent-sweep kernels set non-zero when an
+ * inter-CTA wait timed out (results are then invalid; never a hang).  Callers that synchronise anyway
+ * (e.g. for the per-step log line) should read it. */
+size_t ctcb_brnn_error_flag_offset(const ctcb_brnn_config *cfg);
 
 int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out);
 void ctcb_brnn_destroy(ctcb_brnn *h);

@@ -202,6 +202,11 @@ extern "C" size_t ctcb_brnn_workspace_bytes(const ctcb_brnn_config *cfg) {
     return ws_layout(cfg).total;
 }
 
+extern "C" size_t ctcb_brnn_error_flag_offset(const ctcb_brnn_config *cfg) {
+    if (!valid_cfg(cfg)) return 0;
+    return ws_layout(cfg).counters;
+}
+
 extern "C" int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out) {
     if (!valid_cfg(cfg) || !out) return set_error(CTCB_EINVAL, "ctcb_brnn_create: bad config");
     ctcb_brnn *h = new (std::nothrow) ctcb_brnn;

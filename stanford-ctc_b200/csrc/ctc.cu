@@ -263,7 +263,11 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
                     double2 av[P];
 #pragma unroll
                     for (int j = 0; j < P; ++j) av[j] = an[j];
-                    {   // prefetch the earlier frame (t-1, clamped: the value is unused at t = 0)
+                    {   // pull the alpha-tilde row needed 4 frames from now into L1 (the spill sits in L2/HBM), then
+                        // load the row of the next frame (t-1, clamped: the value is unused at t = 0)
+                        const double *pf = wsu + (int64_t)max(t - 4, 0) * LP + lane * 2 * P;
+                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                        if (P > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 16));
                         const int tp = max(t - 1, 0);
                         const double2 *arow = reinterpret_cast<const double2 *>(wsu + (int64_t)tp * LP) + lane * P;
 #pragma unroll
@@ -449,6 +453,9 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     const size_t per_warp = (size_t)3 * TT * a.Kp * sizeof(float);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
+    // small batches (the training step): spread the utterances over the SMs instead of packing 8 per CTA --
+    // each warp is a latency-bound serial chain and gains from an otherwise idle SM
+    while (wpb > 1 && (B + wpb - 1) / wpb < 2 * num_sms()) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > 200 * 1024)
         return set_error(CTCB_EINVAL, "ctcb_ctc_loss_grad_f32: K=%d too large for the shared-memory tile", K);

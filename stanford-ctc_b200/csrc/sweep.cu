@@ -243,8 +243,8 @@ int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *p
             bool handled = false;
             CTCB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, st));
             const int rc = run_sweep_cluster(mode, T, B, H, Tlen, pre, Wf, Wb, outF, outB, actF, actB, maxAct, counters, st, &handled);
-            if (rc != CTCB_OK) return rc;
-            if (handled) return CTCB_OK;
+            if (rc == CTCB_OK && handled) return CTCB_OK;
+            if (rc != CTCB_OK) cudaGetLastError();   // cluster launch refused: fall through to the general kernel
         }
     }
     const int slices = (H + SW_ROWS - 1) / SW_ROWS;

@@ -183,12 +183,24 @@ class NNet:
             self.grads = None
             self.stats = None
         nbytes = lib.ctcb_brnn_workspace_bytes(ctypes.byref(self._cfg))
-        self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.dev)
+        self._ws = torch.zeros(nbytes, dtype=torch.uint8, device=self.dev)
+        off = lib.ctcb_brnn_error_flag_offset(ctypes.byref(self._cfg))
+        self._errflag = self._ws[off:off + 4].view(torch.int32)      # set by the sweep kernels on a wait timeout
         self._batch = DeviceBatch(torch, self.dev, self.maxBatch, self.maxUtts, self.inputDim, self.maxLabels)
+        self._batch_alt = None      # second staging buffer, created on first use by SGD.run's prefetch
         self._cost = torch.zeros(self.maxUtts, dtype=torch.float32, device=self.dev)
         self._skip = torch.zeros(self.maxUtts, dtype=torch.int32, device=self.dev)
         self._regcost = torch.zeros(1, dtype=torch.float32, device=self.dev)
         self._probs = None
+
+    def swap_batches(self):
+        """Double buffering of the staging area: returns the buffer that is NOT the current one and makes it
+        current (SGD.run packs minibatch i+1 into it while the device still works on minibatch i)."""
+        if self._batch_alt is None:
+            self._batch_alt = DeviceBatch(self._torch, self.dev, self.maxBatch, self.maxUtts, self.inputDim,
+                                          self.maxLabels)
+        self._batch, self._batch_alt = self._batch_alt, self._batch
+        return self._batch
 
     def paramCount(self):
         return int(sum(w.numel() + b.numel() for w, b in self.stack))
@@ -226,8 +238,11 @@ class NNet:
         Returns (costs float64[B], self.grad, skips bool[B]); the L2 term is in self.regcost."""
         self._batch.pack(datas, labelss).upload()
         cost, skip = self.costAndGradDevice(self._batch)
-        host = self._torch.cat([cost, skip.to(self._torch.float32), self._regcost]).cpu().numpy()
+        host = self._torch.cat([cost, skip.to(self._torch.float32), self._regcost,
+                                self._errflag.to(self._torch.float32)]).cpu().numpy()
         B = len(datas)
+        if host[2 * B + 1] != 0:
+            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[2 * B + 1]))
         self.regcost = float(host[2 * B])
         return host[:B].astype(np.float64), self.grad, host[B:2 * B] != 0
 

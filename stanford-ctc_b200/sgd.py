@@ -97,81 +97,102 @@ class SGD:
     def _momentum_now(self):
         return 0.5 if self.it <= 10 else self.momentum                  # sgd.py:64-74
 
-    def run(self, data_dict, alis, keys, sizes):
-        """Runs stochastic gradient descent with nesterov acceleration.  Model is objective."""
+    def _prepare(self, data_dict, alis, chunk, rank, world):
+        """Host side of one step: the reference's length checks (sgd.py:76-88), sharding over ranks, packing into
+        the idle staging buffer and the asynchronous H2D copy."""
+        m = self.model
+        datas, labels, used = [], [], []
+        for k in chunk:
+            mb_data = data_dict[k]
+            if mb_data.shape[1] > self.maxBatch:
+                logging.info("SKIPPING utt exceeds batch length (Utterance length %d)." % mb_data.shape[1])
+                continue
+            mb_labels = np.array(alis[k], dtype=np.int32)
+            if mb_data.shape[1] < mb_labels.shape[0]:
+                logging.info("SKIPPING utt frames less than label length "
+                             "(Utterance length %d, Num Labels %d)." % (mb_data.shape[1], mb_labels.shape[0]))
+                continue
+            datas.append(mb_data)
+            labels.append(mb_labels)
+            used.append(k)
+        if world > 1:          # shard the step's utterances over the ranks
+            datas, labels, used = (parallel.shard(x, rank, world) for x in (datas, labels, used))
+        batch = None
+        if datas:
+            batch = m.swap_batches().pack(datas, labels).upload()
+        return dict(batch=batch, used=used, nlab=sum(l.shape[0] for l in labels),
+                    nframes=sum(d.shape[1] for d in datas))
+
+    def _launch(self, prep, dist):
+        """Device side of one step (never synchronises)."""
+        m = self.model
+        self.it += 1
+        mom = self._momentum_now()
+        if prep["batch"] is not None:
+            self.step_device(prep["batch"], mom)
+        else:                  # this rank has no utterance this step: contribute zeros to the all-reduce
+            st = _ctcb.current_stream()
+            m.grads_ext.zero_()
+            parallel.allreduce_sum(dist, m.grads_ext)
+            check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch), st))
+            check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, st))
+            check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams, float(mom),
+                                                 float(self.alpha), float(self.maxGNorm), ptr(self._gnorm2),
+                                                 ptr(m.stats), st))
+
+    def _finish(self, prep, rank):
+        """One small D2H per step for the log line, as the reference prints every iteration (sgd.py:113-167)."""
         torch = self._torch
         m = self.model
+        host = torch.cat([m.stats, self._gnorm2, m._regcost, m._errflag.to(torch.float32)]).cpu().numpy()
+        if host[6] != 0:
+            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[6]))
+        nvalid, costsum = float(host[0]), float(host[1])
+        gnorm = float(np.sqrt(host[4]))
+        m.regcost = float(host[5])
+        if nvalid == 0:
+            logging.info("SKIPPING: Keys=%s" % (",".join(str(k) for k in prep["used"])))
+            return
+        cost = costsum / nvalid + (m.regcost if m.reg > 0 else 0.0)
+        if np.isfinite(cost):
+            # compute exponentially weighted cost                   sgd.py:113-119
+            if len(self.expcost) > 0:
+                self.expcost.append(.01 * cost + .99 * self.expcost[-1])
+            else:
+                self.expcost.append(cost)
+            self.costt.append(cost)
+            if m.reg > 0.0:
+                rc = m.regcost
+                if len(self.regcost) > 0:
+                    self.regcost.append(0.01 * rc + 0.99 * self.regcost[-1])
+                else:
+                    self.regcost.append(rc)
+        if self.verbose and rank == 0:
+            print("Iter %d : Cost=%.4f, ExpCost=%.4f, GradNorm=%.4f, SeqLen=%d, NumFrames=%d."
+                  % (self.it, cost, self.expcost[-1] if self.expcost else float('nan'), gnorm,
+                     prep["nlab"], prep["nframes"]))
+
+    def run(self, data_dict, alis, keys, sizes):
+        """Runs stochastic gradient descent with nesterov acceleration.  Model is objective.
+        Steps are software-pipelined: while the device works on minibatch i the host checks, packs and
+        uploads minibatch i+1 into the second staging buffer; the per-step log read-back follows."""
         dist, rank, world = self._world()
 
         # randomly select minibatch
         random.shuffle(keys)
 
         step = max(1, self.batchSize)
-        for k0 in range(0, len(keys), step):
-            chunk = keys[k0:k0 + step]
-            self.it += 1
-            mom = self._momentum_now()
-
-            datas, labels, used = [], [], []
-            for k in chunk:
-                mb_data = data_dict[k]
-                if mb_data.shape[1] > self.maxBatch:
-                    logging.info("SKIPPING utt exceeds batch length (Utterance length %d)." % mb_data.shape[1])
-                    continue
-                mb_labels = np.array(alis[k], dtype=np.int32)
-                if mb_data.shape[1] < mb_labels.shape[0]:
-                    logging.info("SKIPPING utt frames less than label length "
-                                 "(Utterance length %d, Num Labels %d)." % (mb_data.shape[1], mb_labels.shape[0]))
-                    continue
-                datas.append(mb_data)
-                labels.append(mb_labels)
-                used.append(k)
-            if world > 1:          # shard the step's utterances over the ranks
-                datas, labels, used = (parallel.shard(x, rank, world) for x in (datas, labels, used))
-            if world == 1 and not datas:
-                continue
-
-            if datas:
-                m._batch.pack(datas, labels).upload()
-            else:                  # this rank has no utterance this step: contribute zeros
-                m._batch.B = 0
-            if m._batch.B > 0:
-                self.step_device(m._batch, mom)
+        chunks = [keys[k0:k0 + step] for k0 in range(0, len(keys), step)]
+        if not chunks:
+            return
+        prep = self._prepare(data_dict, alis, chunks[0], rank, world)
+        for i in range(len(chunks)):
+            active = (prep["batch"] is not None) or world > 1
+            if active:
+                self._launch(prep, dist)
             else:
-                m.grads_ext.zero_()
-                parallel.allreduce_sum(dist, m.grads_ext)
-                check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch),
-                                         _ctcb.current_stream()))
-                check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, _ctcb.current_stream()))
-                check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams,
-                                                     float(mom), float(self.alpha), float(self.maxGNorm),
-                                                     ptr(self._gnorm2), ptr(m.stats), _ctcb.current_stream()))
-
-            # one small D2H per step for the log line, as the reference prints every iteration
-            host = torch.cat([m.stats, self._gnorm2, m._regcost]).cpu().numpy()
-            nvalid, costsum, nskip = float(host[0]), float(host[1]), float(host[2])
-            gnorm = float(np.sqrt(host[4]))
-            m.regcost = float(host[5])
-            if nvalid == 0:
-                logging.info("SKIPPING: Keys=%s" % (",".join(str(k) for k in used)))
-                continue
-            cost = costsum / nvalid + (m.regcost if m.reg > 0 else 0.0)
-
-            if np.isfinite(cost):
-                # compute exponentially weighted cost                   sgd.py:113-119
-                if len(self.expcost) > 0:
-                    self.expcost.append(.01 * cost + .99 * self.expcost[-1])
-                else:
-                    self.expcost.append(cost)
-                self.costt.append(cost)
-                if m.reg > 0.0:
-                    rc = m.regcost
-                    if len(self.regcost) > 0:
-                        self.regcost.append(0.01 * rc + 0.99 * self.regcost[-1])
-                    else:
-                        self.regcost.append(rc)
-
-            if self.verbose and rank == 0 and self.it % 1 == 0:
-                print("Iter %d : Cost=%.4f, ExpCost=%.4f, GradNorm=%.4f, SeqLen=%d, NumFrames=%d."
-                      % (self.it, cost, self.expcost[-1] if self.expcost else float('nan'), gnorm,
-                         sum(l.shape[0] for l in labels), sum(d.shape[1] for d in datas)))
+                self.it += 1               # the reference counts skipped utterances too (sgd.py:71)
+            nxt = self._prepare(data_dict, alis, chunks[i + 1], rank, world) if i + 1 < len(chunks) else None
+            if active:
+                self._finish(prep, rank)
+            prep = nxt
