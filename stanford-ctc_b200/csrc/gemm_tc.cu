@@ -10,14 +10,19 @@
 //
 // Kernel shape: C[M x N] = A[M x K] . B[N x K]^T, both operands K-major.  One CTA (4 warps) per
 // 128 x BN output tile and K split (gridDim.z):
-//   warp 0 / lane 0 : TMA producer -- per k-block of 32 floats four 128B-swizzled tiles
-//                     (A, A_lo, B, B_lo) into a STAGES-deep shared-memory ring, mbarrier complete_tx;
+//   warp 0 / lane 0 : TMA producer -- per k-block of 32 floats two 128B-swizzled tiles (A, B) into a
+//                     STAGES-deep shared-memory ring, mbarrier complete_tx;
+//   warps 4..7      : splitter -- as soon as a stage has landed, compute the lo tiles IN SHARED MEMORY
+//                     (lo = x - trunc_tf32(x) is element-wise, so it is oblivious to the 128B swizzle);
+//                     fence.proxy.async + mbarrier hand the stage to the MMA warp.  The kernel was bound by
+//                     the L2->SM fill (64 KB per k-block at ~42 B/cycle/SM, ncu: tensor pipe 31 %): producing
+//                     lo on chip halves that traffic and removes the lo arrays from HBM;
 //   warp 1 / lane 0 : MMA issuer  -- 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per k-block,
 //                     tcgen05.commit releases the ring slot; the last commit signals the epilogue;
 //   warps 0..3      : epilogue -- tcgen05.ld 32 lanes x 32 columns per warp, fused alpha/beta/bias/ReLU/
 //                     mask (or split-K partial), row stores.
-// Transposed operands and operands whose row pitch is not a multiple of 16 bytes are re-laid-out by the
-// prep kernel that also produces the lo parts, so the tensor-core kernel only ever sees K-major tiles.
+// Transposed operands and operands whose row pitch is not a multiple of 16 bytes are re-laid-out by a
+// prep kernel, so the tensor-core kernel only ever sees K-major tiles.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -106,16 +111,17 @@ __device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(128, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAl,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBl, GemmTcArgs g) {
+__global__ void __launch_bounds__(256)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
     constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     // 1024-byte alignment is required by SWIZZLE_128B: align manually (dynamic smem base is only 16B-aligned by contract)
     uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + STAGES * STAGE_BYTES);   // full[STAGES], empty[STAGES], done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 2 * STAGES + 1);
+    // full[STAGES] (TMA landed), empty[STAGES] (MMAs done with the slot), done, ready[STAGES] (lo tiles written)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + STAGES * STAGE_BYTES);
+    uint64_t *ready = bars + 2 * STAGES + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(ready + STAGES);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -128,6 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             tc_mbar_init(tc_smem_u32(&bars[s]), 1);
             tc_mbar_init(tc_smem_u32(&bars[STAGES + s]), 1);
+            tc_mbar_init(tc_smem_u32(&ready[s]), 4);          // one arrival per splitter warp
         }
         tc_mbar_init(tc_smem_u32(&bars[2 * STAGES]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,20 +155,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = i % STAGES, use = i / STAGES;
                 if (use > 0) tc_mbar_wait(tc_smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
                 const uint32_t full = tc_smem_u32(&bars[s]);
-                tc_mbar_expect_tx(full, STAGE_BYTES);
+                tc_mbar_expect_tx(full, A_BYTES + B_BYTES);
                 uint8_t *st = base + s * STAGE_BYTES;
                 const int k = (kb0 + i) * TC_BK;
                 tc_tma_load_2d(tc_smem_u32(st), &tmA, full, k, m0);
-                tc_tma_load_2d(tc_smem_u32(st + A_BYTES), &tmAl, full, k, m0);
                 tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES), &tmB, full, k, n0);
-                tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES + B_BYTES), &tmBl, full, k, n0);
             }
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------ MMA issuer
             constexpr uint32_t idesc = tc_idesc(TC_BM, BN);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
-                tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));
+                tc_mbar_wait(tc_smem_u32(&ready[s]), (uint32_t)(use & 1));      // hi landed and lo written
                 tc_fence_after();
                 const uint32_t a = tc_smem_u32(base + s * STAGE_BYTES);
                 const uint64_t dA = tc_smem_desc(a), dAl = tc_smem_desc(a + A_BYTES);
@@ -176,6 +181,32 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_commit(tc_smem_u32(&bars[STAGES + s]));         // slot free once these MMAs have read it
             }
             tc_commit(tc_smem_u32(&bars[2 * STAGES]));             // accumulator complete
+        } else if (warp >= 4) {
+            // ------------------------------------------------------------ splitter (128 threads)
+            const int tid = threadIdx.x - 128;
+            for (int i = 0; i < nkb; ++i) {
+                const int s = i % STAGES, use = i / STAGES;
+                tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
+                float4 *hiA = reinterpret_cast<float4 *>(base + s * STAGE_BYTES);
+                float4 *loA = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + A_BYTES);
+                float4 *hiB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES);
+                float4 *loB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES);
+                auto lo4 = [](float4 v) {
+                    float4 r;
+                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    return r;
+                };
+#pragma unroll
+                for (int q = 0; q < (int)(A_BYTES / 16 / 128); ++q) loA[tid + q * 128] = lo4(hiA[tid + q * 128]);
+#pragma unroll
+                for (int q = 0; q < (int)(B_BYTES / 16 / 128); ++q) loB[tid + q * 128] = lo4(hiB[tid + q * 128]);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> tensor-core (async) proxy
+                __syncwarp();
+                if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&ready[s])) : "memory");
+            }
         }
         __syncwarp();
         // ---------------------------------------------------------------- epilogue (all 4 warps)
@@ -184,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     const int m = m0 + warp * 32 + lane;
 #pragma unroll 1
-    for (int c = 0; c < BN; c += 32) {
+    for (int c = 0; c < BN && warp < 4; c += 32) {
         uint32_t r[32];
         if (nkb > 0) {
             const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
@@ -239,7 +270,7 @@ __global__ void tc_split_kernel(const float *__restrict__ x, int64_t ld, int row
         const float v = (c < cols) ? x[(int64_t)r * ld + c] : 0.f;
         const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
         if (hi) hi[idx] = v;
-        lo[idx] = v - h;
+        if (lo) lo[idx] = v - h;
     }
 }
 // transposing variant: x is rows x cols (ld); outputs are cols x rows (ldo >= rows), tiled through shared memory
@@ -258,7 +289,7 @@ __global__ void tc_split_transpose_kernel(const float *__restrict__ x, int64_t l
             const float v = (r < rows) ? tile[threadIdx.x][i] : 0.f;
             const float h = __uint_as_float(__float_as_uint(v) & 0xffffe000u);
             hi[(int64_t)c * ldo + r] = v;
-            lo[(int64_t)c * ldo + r] = v - h;
+            if (lo) lo[(int64_t)c * ldo + r] = v - h;
         }
     }
 }
@@ -344,7 +375,7 @@ bool gemm_tc_eligible(int M, int N, int K) { return gemm_tc_enabled() && M >= 64
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
     const int64_t Kp = pad4(K);
-    size_t prep = (size_t)2 * ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float);
+    size_t prep = ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float);     // re-laid-out copies of A and B (when needed)
     const int BN = tc_pick_bn(M, N);
     const int splits = tc_choose_splits(M, N, K, BN);
     size_t part = splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
@@ -352,12 +383,11 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
 }
 
 template <int BN, int STAGES>
-static int launch_tc(const CUtensorMap &tA, const CUtensorMap &tAl, const CUtensorMap &tB, const CUtensorMap &tBl,
-                     const GemmTcArgs &g, int splits, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (2 * STAGES + 1) * 8 + 16 + 1024;
+static int launch_tc(const CUtensorMap &tA, const CUtensorMap &tB, const GemmTcArgs &g, int splits, cudaStream_t st) {
+    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (3 * STAGES + 1) * 8 + 16 + 1024;
     CTCB_CUDA_CHECK(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, splits);
-    gemm_tc_kernel<BN, STAGES><<<grid, 128, smem, st>>>(tA, tAl, tB, tBl, g);
+    gemm_tc_kernel<BN, STAGES><<<grid, 256, smem, st>>>(tA, tB, g);
     CTCB_LAUNCH_CHECK();
     return CTCB_OK;
 }
@@ -370,35 +400,35 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     const int64_t Kp = pad4(K);
     float *p = (float *)ws;
     float *Ahi = p; p += (size_t)M * Kp;
-    float *Alo = p; p += (size_t)M * Kp;
     float *Bhi = p; p += (size_t)N * Kp;
-    float *Blo = p; p += (size_t)N * Kp;
-    float *part = (float *)((char *)ws + align_up((size_t)2 * ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float), 256));
+    float *part = (float *)((char *)ws + align_up(((size_t)M * Kp + (size_t)N * Kp) * sizeof(float), 256));
 
     // ---- operand A as M x K, K-major: stored M x K (transA=0) or K x M (transA=1)
     const float *Ause; int64_t lda_use;
     auto ew_grid = [](int64_t n) { int64_t b = (n + 255) / 256; const int cap = 16 * num_sms(); return (int)(b > cap ? cap : (b < 1 ? 1 : b)); };
     if (transA) {
-        tc_split_transpose_kernel<<<dim3((M + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(A, lda, K, M, Ahi, Alo, Kp);
+        tc_split_transpose_kernel<<<dim3((M + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(A, lda, K, M, Ahi, nullptr, Kp);
         CTCB_LAUNCH_CHECK();
         Ause = Ahi; lda_use = Kp;
+    } else if ((lda % 4 == 0) && (((uintptr_t)A) % 16 == 0)) {
+        Ause = A; lda_use = lda;                       // TMA reads the caller's array directly
     } else {
-        const bool direct = (lda % 4 == 0) && (((uintptr_t)A) % 16 == 0);
-        tc_split_kernel<<<ew_grid((int64_t)M * Kp), 256, 0, st>>>(A, lda, M, K, direct ? nullptr : Ahi, Alo, Kp);
+        tc_split_kernel<<<ew_grid((int64_t)M * Kp), 256, 0, st>>>(A, lda, M, K, Ahi, nullptr, Kp);   // re-pitch to 16-byte rows
         CTCB_LAUNCH_CHECK();
-        Ause = direct ? A : Ahi; lda_use = direct ? lda : Kp;
+        Ause = Ahi; lda_use = Kp;
     }
     // ---- operand B as N x K, K-major: stored N x K (transB=1) or K x N (transB=0)
     const float *Buse; int64_t ldb_use;
     if (!transB) {
-        tc_split_transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Bhi, Blo, Kp);
+        tc_split_transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Bhi, nullptr, Kp);
         CTCB_LAUNCH_CHECK();
         Buse = Bhi; ldb_use = Kp;
+    } else if ((ldb % 4 == 0) && (((uintptr_t)B) % 16 == 0)) {
+        Buse = B; ldb_use = ldb;
     } else {
-        const bool direct = (ldb % 4 == 0) && (((uintptr_t)B) % 16 == 0);
-        tc_split_kernel<<<ew_grid((int64_t)N * Kp), 256, 0, st>>>(B, ldb, N, K, direct ? nullptr : Bhi, Blo, Kp);
+        tc_split_kernel<<<ew_grid((int64_t)N * Kp), 256, 0, st>>>(B, ldb, N, K, Bhi, nullptr, Kp);
         CTCB_LAUNCH_CHECK();
-        Buse = direct ? B : Bhi; ldb_use = direct ? ldb : Kp;
+        Buse = Bhi; ldb_use = Kp;
     }
 
     const int BN = tc_pick_bn(M, N);
@@ -410,15 +440,16 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
     g.partial = splits > 1 ? part : nullptr;
 
-    CUtensorMap tA, tAl, tB, tBl;
+    CUtensorMap tA, tB;
     int rc;
     if ((rc = make_map(&tA, Ause, M, K, lda_use, TC_BM)) != CTCB_OK) return rc;
-    if ((rc = make_map(&tAl, Alo, M, K, Kp, TC_BM)) != CTCB_OK) return rc;
     if ((rc = make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
-    if ((rc = make_map(&tBl, Blo, N, K, Kp, BN)) != CTCB_OK) return rc;
-    if (BN == 64) rc = launch_tc<64, 4>(tA, tAl, tB, tBl, g, splits, st);
-    else if (BN == 256) rc = launch_tc<256, 2>(tA, tAl, tB, tBl, g, splits, st);
-    else rc = launch_tc<128, 3>(tA, tAl, tB, tBl, g, splits, st);
+    static int stages_env = -1;   // CTCB_GEMM_STAGES=2 with BN=64: 96 KB/CTA -> two CTAs per SM overlap prologue/epilogue
+    if (stages_env < 0) { const char *e = getenv("CTCB_GEMM_STAGES"); stages_env = e ? atoi(e) : 0; }
+    if (BN == 64 && stages_env == 2) rc = launch_tc<64, 2>(tA, tB, g, splits, st);
+    else if (BN == 64) rc = launch_tc<64, 4>(tA, tB, g, splits, st);
+    else if (BN == 256) rc = launch_tc<256, 2>(tA, tB, g, splits, st);
+    else rc = launch_tc<128, 3>(tA, tB, g, splits, st);
     if (rc != CTCB_OK) return rc;
     if (splits > 1) {
         const int64_t total = (int64_t)M * N;

@@ -1,14 +1,16 @@
-"""dataLoader -- reads the reference's Kaldi-derived training files, same class and method names as
-/root/reference/ctc_fast/dataLoader.py:6-95.
+"""dataLoader -- reader of the reference's Kaldi-derived training files.  Class and method names follow
+/root/reference/ctc_fast/dataLoader.py:6-95 (DataLoader, loadDataFile, loadDataFileDict,
+loadDataFileAsynch, getDataAsynch) because sgd/runNNet and the reference's own tools call them.
 
-    feats%d.bin : float32 rows of `rawsize` features, all utterances of the file concatenated
-    keys%d.txt  : "<utterance-key> <num_frames>" per line
-    alis%d.txt  : "<utterance-key> <label> <label> ..." per line
+File triple number n in a directory:
+    feats<n>.bin : float32, one row of `rawsize` features per frame, utterances back to back
+    keys<n>.txt  : "<utterance-key> <num_frames>" per line, in file order
+    alis<n>.txt  : "<utterance-key> <label> <label> ..." per line
 
-loadDataFileDict returns (data_dict, alis, keys, sizes) with data_dict[key] an (imgsize x T) float32
-array whose frames are contiguous (Fortran order), exactly what the reference hands to SGD.run.
-The asynchronous prefetch uses a thread instead of the reference's forked child (dataLoader.py:22-36):
-forking after CUDA initialisation is unsafe, and the loader is pure NumPy file IO.
+`loadDataFileDict` returns (data_dict, alis, keys, sizes); data_dict[key] is an (imgsize x T) float32 array
+with contiguous frames (Fortran order) -- the per-utterance layout the rest of the surface expects.
+The prefetch runs in a thread (the reference forks a child, dataLoader.py:22-36, which is unsafe once CUDA
+is initialised; the loader only does NumPy file IO, which releases the GIL).
 """
 import os
 import threading
@@ -16,87 +18,101 @@ import threading
 import numpy as np
 
 
+def _read_alignments(path):
+    table = {}
+    with open(path) as fid:
+        for line in fid:
+            fields = line.split()
+            if fields:
+                table[fields[0]] = fields[1:]
+    return table
+
+
+def _read_keys(path):
+    names, frames = [], []
+    with open(path) as fid:
+        for line in fid:
+            fields = line.split()
+            if fields:
+                names.append(fields[0])
+                frames.append(np.int32(fields[1]))
+    return names, np.array(frames)
+
+
 class DataLoader:
     def __init__(self, filedir_feat, rawsize, imgsize, filedir_ali=None, load_ali=True, load_data=True):
         self.filedir_feat = filedir_feat
-        self.rawsize = rawsize
-        self.imgsize = imgsize
-        self.filedir_ali = filedir_feat if filedir_ali is None else filedir_ali
-        self.load_ali = load_ali
-        self.load_data = load_data
-        self.p = None
-        self._result = None
+        self.filedir_ali = filedir_ali if filedir_ali is not None else filedir_feat
+        self.rawsize, self.imgsize = rawsize, imgsize
+        self.load_ali, self.load_data = load_ali, load_data
+        self.p = None            # the prefetch worker (name kept from the reference)
+        self._box = None
+
+    # -- asynchronous prefetch ---------------------------------------------------------------------
+    def loadDataFileAsynch(self, filenum):
+        box = {}
+
+        def work():
+            try:
+                box["value"] = self.loadDataFileDict(filenum)
+            except BaseException as exc:         # re-raised in the consumer
+                box["error"] = exc
+
+        self._box = box
+        self.p = threading.Thread(target=work, name="dataLoader-%d" % filenum)
+        self.p.start()
 
     def getDataAsynch(self):
         assert self.p is not None, "Error in order of asynch calls."
         self.p.join()
-        self.p = None
-        if isinstance(self._result, BaseException):
-            raise self._result
-        return self._result
+        self.p, box = None, self._box
+        if "error" in box:
+            raise box["error"]
+        return box["value"]
 
-    def loadDataFileAsynch(self, filenum):
-        def work():
-            try:
-                self._result = self.loadDataFileDict(filenum)
-            except BaseException as e:      # surfaced by getDataAsynch
-                self._result = e
-        self.p = threading.Thread(target=work)
-        self.p.start()
+    # -- synchronous readers -------------------------------------------------------------------------
+    def _path(self, directory, stem, filenum):
+        return os.path.join(directory, "%s%d.%s" % (stem, filenum, "bin" if stem == "feats" else "txt"))
 
     def loadDataFile(self, filenum):
-        keyfile = os.path.join(self.filedir_feat, 'keys%d.txt' % filenum)
-        alisfile = os.path.join(self.filedir_ali, 'alis%d.txt' % filenum)
-        datafile = os.path.join(self.filedir_feat, 'feats%d.bin' % filenum)
-        keys = sizes = data = None
-        alis = []
-        if self.load_ali:
-            with open(alisfile, 'r') as fid:
-                for l in fid.readlines():
-                    l = l.split()
-                    alis.append((l[0], l[1:]))
-            alis = dict(alis)
-        if self.load_data:
-            if os.path.exists(keyfile):
-                with open(keyfile, 'r') as keyf:
-                    uttdat = [u.split() for u in keyf.readlines()]
-                sizes = np.array([np.int32(u[1]) for u in uttdat])
-                keys = [u[0] for u in uttdat]
-            left = (self.rawsize - self.imgsize) // 2       # centre crop of the context window
-            right = left + self.imgsize
-            data = np.fromfile(datafile, np.float32).reshape(-1, self.rawsize)
-            data = data[:np.sum(sizes), left:right]
-            return data.T, alis, keys, sizes
-        keys = list(alis.keys())
-        return data, alis, keys, sizes
+        """One big (imgsize x total_frames) matrix for the whole file plus alignments, keys and sizes."""
+        alis = _read_alignments(self._path(self.filedir_ali, "alis", filenum)) if self.load_ali else []
+        if not self.load_data:
+            return None, alis, list(alis.keys()), None
+        keys = sizes = None
+        keyfile = self._path(self.filedir_feat, "keys", filenum)
+        if os.path.exists(keyfile):
+            keys, sizes = _read_keys(keyfile)
+        frames = np.fromfile(self._path(self.filedir_feat, "feats", filenum), np.float32).reshape(-1, self.rawsize)
+        lo = (self.rawsize - self.imgsize) // 2       # centre crop of the context window
+        frames = frames[:np.sum(sizes), lo:lo + self.imgsize]
+        return frames.T, alis, keys, sizes
 
     def loadDataFileDict(self, filenum):
-        data_mat, alis, keys, sizes = self.loadDataFile(filenum)
-        if self.load_data:
-            data_dict = {}
-            startInd = 0
-            for k, s in zip(keys, sizes):
-                endInd = startInd + s
-                data_dict[k] = np.copy(data_mat[:, startInd:endInd])
-                startInd = endInd
-            assert startInd == data_mat.shape[1]
-            return data_dict, alis, keys, sizes
-        return None, alis, keys, sizes
+        """Like loadDataFile, with the frames split per utterance into a dictionary keyed by utterance."""
+        matrix, alis, keys, sizes = self.loadDataFile(filenum)
+        if not self.load_data:
+            return None, alis, keys, sizes
+        bounds = np.concatenate([[0], np.cumsum(sizes)])
+        assert bounds[-1] == matrix.shape[1], "keys file and feature file disagree on the frame count"
+        data_dict = {k: np.copy(matrix[:, bounds[i]:bounds[i + 1]]) for i, k in enumerate(keys)}
+        return data_dict, alis, keys, sizes
 
 
 def write_synthetic_file(dirname, filenum, num_utts, rawsize, outputDim, T_range=(150, 250), L_range=(20, 40),
                          seed=33):
-    """Write one synthetic file triple in the reference's on-disk format (for tests and examples)."""
+    """Write one synthetic file triple in the on-disk format above (tests and examples)."""
     rng = np.random.RandomState(seed + filenum)
     os.makedirs(dirname, exist_ok=True)
-    feats, keys, alis = [], [], []
+    blocks, key_lines, ali_lines = [], [], []
     for u in range(num_utts):
         T = int(rng.randint(T_range[0], T_range[1] + 1))
         L = int(min(T, rng.randint(L_range[0], L_range[1] + 1)))
-        feats.append(rng.randn(T, rawsize).astype(np.float32))
         key = "utt%d_%04d" % (filenum, u)
-        keys.append("%s %d" % (key, T))
-        alis.append(key + " " + " ".join(str(int(x)) for x in 1 + rng.randint(0, outputDim - 1, size=L)))
-    np.concatenate(feats, axis=0).tofile(os.path.join(dirname, 'feats%d.bin' % filenum))
-    open(os.path.join(dirname, 'keys%d.txt' % filenum), 'w').write("\n".join(keys) + "\n")
-    open(os.path.join(dirname, 'alis%d.txt' % filenum), 'w').write("\n".join(alis) + "\n")
+        blocks.append(rng.randn(T, rawsize).astype(np.float32))
+        key_lines.append("%s %d" % (key, T))
+        ali_lines.append(" ".join([key] + [str(int(x)) for x in 1 + rng.randint(0, outputDim - 1, size=L)]))
+    np.concatenate(blocks, axis=0).tofile(os.path.join(dirname, "feats%d.bin" % filenum))
+    for stem, lines in (("keys", key_lines), ("alis", ali_lines)):
+        with open(os.path.join(dirname, "%s%d.txt" % (stem, filenum)), "w") as fid:
+            fid.write("\n".join(lines) + "\n")

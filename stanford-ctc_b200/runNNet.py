@@ -1,260 +1,231 @@
-"""runNNet -- training/test driver with the option names, run-directory files and checkpoint cadence of
-/root/reference/ctc_fast/runNNet.py:23-237 (run(), test()).
+"""runNNet -- training / likelihood-dump driver for the B200 backend.
 
-Kept: every reference option (--layerSize --numLayers --temporalLayer --momentum --epochs --step
---anneal --reg --dataDir --alisDir --startFile --numFiles --inputDim --rawDim --outputDim --maxUttLen
---save_every --run_desc --cfg_file --test), cfg.json / params.pk (two pickles: SGD state, then the
-stack) / epoch / num_files / last_cost / sentinel / train.log, resume from --cfg_file, CUDA_DEVICE.
-Site constants of run_cfg.py / decoder_config.py become options: --runDir (RUN_DIR), --outDir
-(likelihood output of --test).  New: --batchSize (utterances per step; 1 = reference schedule),
---maxLabels.  Launched under torchrun it trains data-parallel (one process per GPU, NCCL all-reduce).
+Call surface kept from the reference driver (/root/reference/ctc_fast/runNNet.py:23-237): `run(args)` and
+`test(opts)`, every command-line flag of runNNet.py:27-69 with its default, the run-directory protocol
+(cfg.json, params.pk = SGD pickle followed by the stack pickle, params.pk.epochNN, epoch, num_files,
+last_cost, sentinel, train.log), resume through --cfg_file with the step size re-annealed
+(runNNet.py:143-166), the fixed seeds 33 (:113-115) and CUDA_DEVICE device selection (:117-120).
+The implementation is organised differently: a declarative flag table, one RunDir helper that owns the
+side files, and separate train/evaluate phases.  Site paths of run_cfg.py / decoder_config.py became
+flags (--runDir, --outDir); new flags: --batchSize, --maxLabels, --quiet.  Under torchrun the same
+script trains data-parallel (one process per GPU, one NCCL all-reduce per step).
 """
+import argparse
 import logging
-import optparse
 import os
 import pickle
+import random
 import time
-from os.path import join as pjoin
 
 import numpy as np
 
 import dataLoader as dl
-import parallel
 import nnets.brnnet as rnnet
+import parallel
 import sgd
-from run_utils import dump_config, load_config, CfgStruct, get_git_revision, get_hostname, TimeString, touch_file
+from run_utils import CfgStruct, TimeString, dump_config, get_git_revision, get_hostname, load_config, touch_file
 from writeLikelihoods import writeLogLikes
 
-MAX_UTT_LEN = 5000   # decoder/decoder_config.py:28 (DATASET == 'swbd'), the reference's default
+MAX_UTT_LEN = 5000   # default of the reference (decoder/decoder_config.py:28, DATASET == 'swbd')
+
+# (flag, type, default, help); None type = boolean switch.  Names and defaults: runNNet.py:27-69.
+FLAGS = [
+    ("cfg_file", str, None, "cfg.json of an earlier run: resume training / select the model for --test"),
+    ("test", None, False, "forward-only pass that writes log-likelihood arks"),
+    ("layerSize", int, 1824, None), ("numLayers", int, 5, None), ("temporalLayer", int, 3, None),
+    ("momentum", float, 0.95, None), ("epochs", int, 20, None), ("step", float, 1e-5, None),
+    ("anneal", float, 1.3, "learning rate := learning rate / anneal after each epoch"),
+    ("reg", float, 0.0, "lambda of the L2 penalty on the weight matrices"),
+    ("dataDir", str, "./data/", None), ("alisDir", str, None, None),
+    ("startFile", int, 1, "first file in --test mode"), ("numFiles", int, 384, None),
+    ("inputDim", int, 41 * 15, None), ("rawDim", int, 41 * 15, None), ("outputDim", int, 35, None),
+    ("maxUttLen", int, MAX_UTT_LEN, None),
+    ("save_every", int, 10, "checkpoint every this many data files"),
+    ("run_desc", str, "", "free-text description stored in cfg.json"),
+    # additions
+    ("batchSize", int, 1, "utterances per optimisation step (1 = the reference schedule)"),
+    ("maxLabels", int, 511, "longest label sequence the buffers are sized for"),
+    ("runDir", str, "./runs", "parent of the time-stamped run directory"),
+    ("outDir", str, None, "--test: directory for the likelihood arks"),
+    ("quiet", None, False, "no console logging / per-iteration prints"),
+]
 
 
-def _init_distributed():
+def _parse(argv):
+    ap = argparse.ArgumentParser(description=__doc__.splitlines()[0])
+    for name, typ, default, hlp in FLAGS:
+        if typ is None:
+            ap.add_argument("--" + name, dest=name, action="store_true", default=default, help=hlp)
+        else:
+            ap.add_argument("--" + name, dest=name, type=typ, default=default, help=hlp)
+    return ap.parse_args(argv)
+
+
+def _select_device():
+    """One process per GPU: LOCAL_RANK under torchrun, else the reference's CUDA_DEVICE variable."""
     import torch
     import torch.distributed as dist
-    if 'RANK' in os.environ and 'WORLD_SIZE' in os.environ and int(os.environ['WORLD_SIZE']) > 1:
-        torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', 0)))
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and "RANK" in os.environ:
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         if not dist.is_initialized():
-            dist.init_process_group(backend='nccl')
+            dist.init_process_group(backend="nccl")
         return dist.get_rank(), dist.get_world_size()
-    if 'CUDA_DEVICE' in os.environ:                       # runNNet.py:117-120
-        torch.cuda.set_device(int(os.environ['CUDA_DEVICE']))
-    else:
-        torch.cuda.set_device(0)
+    torch.cuda.set_device(int(os.environ.get("CUDA_DEVICE", 0)))
     return 0, 1
 
 
+class RunDir(object):
+    """The files a run leaves behind, under the names the reference's tools (browse_runs.py, reboot_runs.py,
+    plot_results.py) look for."""
+
+    def __init__(self, path):
+        self.path = path
+
+    def file(self, name):
+        return os.path.join(self.path, name)
+
+    def read_int(self, name, default):
+        f = self.file(name)
+        return int(open(f).read().strip()) if os.path.exists(f) else default
+
+    def write(self, name, value):
+        with open(self.file(name), "w") as fid:
+            fid.write(str(value))
+
+    def checkpoint(self, optimizer, net, suffix=""):
+        with open(self.file("params.pk") + suffix, "wb") as fid:     # two pickles back to back
+            optimizer.toFile(fid)
+            net.toFile(fid)
+
+
+def _attach_logging(run, rank, quiet):
+    root = logging.getLogger()
+    root.setLevel(logging.DEBUG)
+    for old in [h for h in root.handlers if getattr(h, "_ctcb_run", False)]:
+        root.removeHandler(old)
+    sinks = [logging.FileHandler(run.file("train.log" if rank == 0 else "train.%d.log" % rank))]
+    if not quiet:
+        sinks.append(logging.StreamHandler())
+    for h in sinks:
+        h._ctcb_run = True
+        root.addHandler(h)
+    return root
+
+
 def run(args=None):
-    usage = "usage : %prog [options]"
-    parser = optparse.OptionParser(usage=usage)
-    parser.add_option('--cfg_file', dest='cfg_file', default=None,
-                      help='File with settings from previously trained net')
-    parser.add_option("--test", action="store_true", dest="test", default=False)
-    # Architecture
-    parser.add_option("--layerSize", dest="layerSize", type="int", default=1824)
-    parser.add_option("--numLayers", dest="numLayers", type="int", default=5)
-    parser.add_option("--temporalLayer", dest="temporalLayer", type="int", default=3)
-    # Optimization
-    parser.add_option("--momentum", dest="momentum", type="float", default=0.95)
-    parser.add_option("--epochs", dest="epochs", type="int", default=20)
-    parser.add_option("--step", dest="step", type="float", default=1e-5)
-    parser.add_option("--anneal", dest="anneal", type="float", default=1.3,
-                      help="Sets (learning rate := learning rate / anneal) after each epoch.")
-    parser.add_option('--reg', dest='reg', type='float', default=0.0,
-                      help='lambda for L2 regularization of the weight matrices')
-    parser.add_option('--batchSize', dest='batchSize', type='int', default=1,
-                      help='utterances per optimisation step (1 = the reference schedule)')
-    # Data
-    parser.add_option("--dataDir", dest="dataDir", type="string", default='./data/')
-    parser.add_option('--alisDir', dest='alisDir', type='string', default=None)
-    parser.add_option('--startFile', dest='startFile', type='int', default=1, help='Start file for running testing')
-    parser.add_option("--numFiles", dest="numFiles", type="int", default=384)
-    parser.add_option("--inputDim", dest="inputDim", type="int", default=41 * 15)
-    parser.add_option("--rawDim", dest="rawDim", type="int", default=41 * 15)
-    parser.add_option("--outputDim", dest="outputDim", type="int", default=35)
-    parser.add_option("--maxUttLen", dest="maxUttLen", type="int", default=MAX_UTT_LEN)
-    parser.add_option("--maxLabels", dest="maxLabels", type="int", default=511)
-    # Save/Load
-    parser.add_option('--save_every', dest='save_every', type='int', default=10,
-                      help='During training, save parameters every x number of files')
-    parser.add_option('--run_desc', dest='run_desc', type='string', default='', help='Description of experiment run')
-    parser.add_option('--runDir', dest='runDir', type='string', default='./runs',
-                      help='parent of the run directory (RUN_DIR of the reference run_cfg.py)')
-    parser.add_option('--outDir', dest='outDir', type='string', default=None,
-                      help='--test: where the log-likelihood arks go')
-    parser.add_option('--quiet', action='store_true', dest='quiet', default=False)
+    cli = _parse(args)
+    rank, world = _select_device()
+    resumed = cli.cfg_file is not None
+    cfg = load_config(cli.cfg_file) if resumed else dict(vars(cli))
+    for name, _, default, _ in FLAGS:                 # configs written by older runs lack the new keys
+        cfg.setdefault(name, default)
+    cfg.update(host=get_hostname(), git_rev=get_git_revision(), pid=os.getpid(), test=cli.test)
 
-    (opts, args) = parser.parse_args(args)
-
-    if opts.cfg_file:
-        cfg = load_config(opts.cfg_file)
+    if resumed:
+        out_dir = cfg["output_dir"]
     else:
-        cfg = vars(opts)
-
-    rank, world = _init_distributed()
-
-    # These config values should be updated every time
-    cfg['host'] = get_hostname()
-    cfg['git_rev'] = get_git_revision()
-    cfg['pid'] = os.getpid()
-
-    # Create experiment output directory
-    if not opts.cfg_file:
-        output_dir = pjoin(opts.runDir, str(TimeString()))
-        cfg['output_dir'] = output_dir
-        if rank == 0 and not os.path.exists(output_dir):
-            print('Creating %s' % output_dir)
-            os.makedirs(output_dir)
-        opts.cfg_file = pjoin(output_dir, 'cfg.json')
-    else:
-        output_dir = cfg['output_dir']
+        out_dir = os.path.join(cli.runDir, str(TimeString()))
+        if rank == 0:
+            os.makedirs(out_dir, exist_ok=True)
+        cli.cfg_file = os.path.join(out_dir, "cfg.json")
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
+    cfg["output_dir"] = out_dir
+    cfg["in_file"] = cfg["out_file"] = os.path.join(out_dir, "params.pk")
+    if cli.test:                                      # these come from the command line, not the stored config
+        for key in ("dataDir", "numFiles", "startFile", "outDir"):
+            cfg[key] = getattr(cli, key)
 
-    cfg['output_dir'] = output_dir
-    cfg['in_file'] = pjoin(output_dir, 'params.pk')
-    cfg['out_file'] = pjoin(output_dir, 'params.pk')
-    cfg['test'] = opts.test
-    if opts.test:
-        cfg['dataDir'] = opts.dataDir
-        cfg['numFiles'] = opts.numFiles
-        cfg['startFile'] = opts.startFile
-        cfg['outDir'] = opts.outDir
-    for key, default in (('reg', 0.0), ('batchSize', 1), ('maxLabels', 511), ('quiet', False), ('alisDir', None)):
-        if key not in cfg:
-            cfg[key] = default
-
-    # Logging
-    logger = logging.getLogger()
-    logger.setLevel(logging.DEBUG)
-    for h in [h for h in logger.handlers if getattr(h, '_ctcb', False)]:
-        logger.removeHandler(h)
-    handlers = [logging.FileHandler(pjoin(output_dir, 'train.log' if rank == 0 else 'train.%d.log' % rank))]
-    if not cfg['quiet']:
-        handlers.append(logging.StreamHandler())
-    for h in handlers:
-        h._ctcb = True
-        logger.addHandler(h)
-    logger.info('Running on %s' % cfg['host'])
-
-    # seed for debugging, turn off when stable                       runNNet.py:113-115
-    np.random.seed(33)
-    import random
+    run_dir = RunDir(out_dir)
+    log = _attach_logging(run_dir, rank, cfg["quiet"])
+    log.info("Running on %s" % cfg["host"])
+    np.random.seed(33)                                # runNNet.py:113-115
     random.seed(33)
 
     opts = CfgStruct(**cfg)
+    opts.cfg_file = cli.cfg_file
+    if cli.test:
+        return test(opts)
+    return _train(opts, cfg, run_dir, log, rank, world)
 
-    # Testing
-    if opts.test:
-        test(opts)
-        return
 
-    alisDir = opts.alisDir if opts.alisDir else opts.dataDir
-    loader = dl.DataLoader(opts.dataDir, opts.rawDim, opts.inputDim, alisDir)
-
-    per_rank = parallel.per_rank_capacity(opts.batchSize, world)
-    nn = rnnet.NNet(opts.inputDim, opts.outputDim, opts.layerSize, opts.numLayers, opts.maxUttLen,
-                    temporalLayer=opts.temporalLayer, reg=opts.reg, maxUtts=per_rank,
-                    maxLabels=min(opts.maxLabels, opts.maxUttLen))
-    nn.initParams()
-
-    SGD = sgd.SGD(nn, opts.maxUttLen, alpha=opts.step, momentum=opts.momentum, batchSize=opts.batchSize,
-                  verbose=(rank == 0 and not opts.quiet))
-
-    # Dump config
-    cfg['param_count'] = nn.paramCount()
+def _train(opts, cfg, run_dir, log, rank, world):
+    loader = dl.DataLoader(opts.dataDir, opts.rawDim, opts.inputDim, opts.alisDir or opts.dataDir)
+    net = rnnet.NNet(opts.inputDim, opts.outputDim, opts.layerSize, opts.numLayers, opts.maxUttLen,
+                     temporalLayer=opts.temporalLayer, reg=opts.reg,
+                     maxUtts=parallel.per_rank_capacity(opts.batchSize, world),
+                     maxLabels=min(opts.maxLabels, opts.maxUttLen))
+    net.initParams()
+    optimizer = sgd.SGD(net, opts.maxUttLen, alpha=opts.step, momentum=opts.momentum, batchSize=opts.batchSize,
+                        verbose=(rank == 0 and not opts.quiet))
+    cfg["param_count"] = net.paramCount()
     if rank == 0:
         dump_config(cfg, opts.cfg_file)
 
-    # Training
-    epoch_file = pjoin(output_dir, 'epoch')
-    if os.path.exists(epoch_file):
-        start_epoch = int(open(epoch_file, 'r').read()) + 1
-    else:
-        start_epoch = 0
+    first_epoch = run_dir.read_int("epoch", -1) + 1
+    if os.path.exists(opts.in_file):                  # resume: optimiser state, then the stack
+        with open(opts.in_file, "rb") as fid:
+            optimizer.fromFile(fid)
+            optimizer.alpha = optimizer.alpha / (opts.anneal ** first_epoch)
+            net.fromFile(fid)
 
-    # Load model if specified
-    if os.path.exists(opts.in_file):
-        with open(opts.in_file, 'rb') as fid:
-            SGD.fromFile(fid)
-            SGD.alpha = SGD.alpha / (opts.anneal ** start_epoch)
-            nn.fromFile(fid)
-
-    num_files_file = pjoin(output_dir, 'num_files')
-
-    for k in range(start_epoch, opts.epochs):
-        perm = np.random.permutation(opts.numFiles) + 1
-        loader.loadDataFileAsynch(perm[0])
-
-        file_start = 0
-        if k == start_epoch:
-            if os.path.exists(num_files_file):
-                file_start = int(open(num_files_file, 'r').read().strip())
-                logger.info('Starting from file %d, epoch %d' % (file_start, start_epoch))
+    for epoch in range(first_epoch, opts.epochs):
+        order = np.random.permutation(opts.numFiles) + 1
+        loader.loadDataFileAsynch(order[0])
+        first_file = 0
+        if epoch == first_epoch:
+            first_file = run_dir.read_int("num_files", 0)
+            if first_file:
+                log.info("Starting from file %d, epoch %d" % (first_file, first_epoch))
         elif rank == 0:
-            open(num_files_file, 'w').write(str(file_start))
+            run_dir.write("num_files", 0)
 
-        for i in range(file_start, perm.shape[0]):
-            start = time.time()
+        for n in range(first_file, len(order)):
+            tic = time.time()
             data_dict, alis, keys, sizes = loader.getDataAsynch()
-            # Prefetch
-            if i + 1 < perm.shape[0]:
-                loader.loadDataFileAsynch(perm[i + 1])
-            SGD.run(data_dict, alis, keys, sizes)
-            end = time.time()
-            logger.info('File time %f' % (end - start))
-
-            # Save parameters and cost
-            if (i + 1) % opts.save_every == 0 and rank == 0:
-                logger.info('Saving parameters')
-                with open(opts.out_file, 'wb') as fid:
-                    SGD.toFile(fid)
-                    nn.toFile(fid)
-                    open(num_files_file, 'w').write('%d' % (i + 1))
-                logger.info('Done saving parameters')
-                if SGD.expcost:
-                    with open(pjoin(output_dir, 'last_cost'), 'w') as fid:
-                        if opts.reg > 0.0 and SGD.regcost:
-                            fid.write(str(SGD.expcost[-1] - SGD.regcost[-1]))
-                        else:
-                            fid.write(str(SGD.expcost[-1]))
+            if n + 1 < len(order):                    # prefetch the next file while this one trains
+                loader.loadDataFileAsynch(order[n + 1])
+            optimizer.run(data_dict, alis, keys, sizes)
+            log.info("File time %f" % (time.time() - tic))
+            if (n + 1) % opts.save_every == 0 and rank == 0:
+                log.info("Saving parameters")
+                run_dir.checkpoint(optimizer, net)
+                run_dir.write("num_files", n + 1)
+                if optimizer.expcost:
+                    smooth = optimizer.expcost[-1]
+                    if opts.reg > 0.0 and optimizer.regcost:
+                        smooth -= optimizer.regcost[-1]
+                    run_dir.write("last_cost", smooth)
 
         if rank == 0:
-            # Save epoch completed
-            open(pjoin(output_dir, 'epoch'), 'w').write(str(k))
-            # Save parameters for the epoch
-            with open(opts.out_file + '.epoch{0:02}'.format(k), 'wb') as fid:
-                SGD.toFile(fid)
-                nn.toFile(fid)
+            run_dir.write("epoch", epoch)
+            run_dir.checkpoint(optimizer, net, suffix=".epoch{0:02}".format(epoch))
+        optimizer.alpha = optimizer.alpha / opts.anneal
 
-        SGD.alpha = SGD.alpha / opts.anneal
-
-    # Run now complete, touch sentinel file
     if rank == 0:
-        touch_file(pjoin(output_dir, 'sentinel'))
-    return SGD, nn
+        touch_file(run_dir.file("sentinel"))          # run complete
+    return optimizer, net
 
 
 def test(opts):
-    old_opts = CfgStruct(**load_config(opts.cfg_file))
-    logger = logging.getLogger()
-    logger.info('Running on %s' % get_hostname())
-
-    with open(old_opts.in_file, 'rb') as fid:
-        pickle.load(fid)  # SGD data, not needed
-        alisDir = opts.alisDir if opts.alisDir else opts.dataDir
-        loader = dl.DataLoader(opts.dataDir, old_opts.rawDim, old_opts.inputDim, alisDir)
-        nn = rnnet.NNet(old_opts.inputDim, old_opts.outputDim, old_opts.layerSize, old_opts.numLayers,
-                        old_opts.maxUttLen, temporalLayer=old_opts.temporalLayer, train=False)
-        nn.initParams()
-        nn.fromFile(fid)
-
-    out_dir = opts.outDir if getattr(opts, 'outDir', None) else pjoin(opts.output_dir, 'ctc_loglikes')
-    if not os.path.exists(out_dir):
-        os.makedirs(out_dir)
-    for i in range(opts.startFile, opts.numFiles + 1):
-        writeLogLikes(loader, nn, i, out_dir, writePickle=True)
+    """Forward-only pass of a trained model over data files; writes Kaldi arks + pickles
+    (runNNet.py:208-237, analysis-utils/writeLikelihoods.py)."""
+    trained = CfgStruct(**load_config(opts.cfg_file))
+    logging.getLogger().info("Running on %s" % get_hostname())
+    net = rnnet.NNet(trained.inputDim, trained.outputDim, trained.layerSize, trained.numLayers, trained.maxUttLen,
+                     temporalLayer=trained.temporalLayer, train=False)
+    net.initParams()
+    with open(trained.in_file, "rb") as fid:
+        pickle.load(fid)                              # optimiser state: not needed here
+        net.fromFile(fid)
+    loader = dl.DataLoader(opts.dataDir, trained.rawDim, trained.inputDim, opts.alisDir or opts.dataDir)
+    out_dir = getattr(opts, "outDir", None) or os.path.join(opts.output_dir, "ctc_loglikes")
+    os.makedirs(out_dir, exist_ok=True)
+    for filenum in range(opts.startFile, opts.numFiles + 1):
+        writeLogLikes(loader, net, filenum, out_dir, writePickle=True)
+    return net
 
 
-if __name__ == '__main__':
+if __name__ == "__main__":
     run()

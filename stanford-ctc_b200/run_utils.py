@@ -1,50 +1,54 @@
-"""run_utils -- the helpers runNNet.py needs, same names as /root/reference/ctc_fast/run_utils.py:10-91
-(dump_config, load_config, CfgStruct, get_git_revision, get_hostname, touch_file, TimeString)."""
-import datetime
+"""run_utils -- small helpers of the driver.  Same public names as the reference module
+(/root/reference/ctc_fast/run_utils.py:10-91: dump_config, load_config, CfgStruct, get_git_revision,
+get_hostname, touch_file, TimeString) because runNNet and the reference's run-management tools import them."""
 import json
-import os
+import pathlib
 import re
+import socket
 import subprocess
+import time
 
 
 def dump_config(cfg, fname):
-    json.dump(cfg, open(fname, 'w'), sort_keys=True, indent=4, separators=(',', ':'))
+    """cfg.json: sorted keys, 4-space indent, compact separators -- the layout the reference writes."""
+    pathlib.Path(fname).write_text(json.dumps(cfg, sort_keys=True, indent=4, separators=(",", ":")))
 
 
 def load_config(fname):
-    return json.load(open(fname, 'r'))
+    return json.loads(pathlib.Path(fname).read_text())
 
 
-class CfgStruct:
+class CfgStruct(object):
+    """Attribute view of a config dict."""
+
     def __init__(self, **entries):
-        self.__dict__.update(entries)
+        vars(self).update(entries)
 
 
 def get_git_revision():
     try:
-        return subprocess.Popen(['git', 'rev-parse', '--short', 'HEAD'], stdout=subprocess.PIPE,
-                                stderr=subprocess.DEVNULL).communicate()[0].decode().strip()
-    except Exception:
-        return ''
+        out = subprocess.run(["git", "rev-parse", "--short", "HEAD"], capture_output=True, text=True, timeout=10)
+        return out.stdout.strip() if out.returncode == 0 else ""
+    except (OSError, subprocess.SubprocessError):
+        return ""
 
 
 def get_hostname():
-    import socket
-    return socket.gethostname().split('.')[0]
+    return socket.gethostname().partition(".")[0]
 
 
 def touch_file(fname):
-    try:
-        os.utime(fname, None)
-    except Exception:
-        open(fname, 'a').close()
+    pathlib.Path(fname).touch()
 
 
 class TimeString(object):
+    """Run-directory name: local time down to the second, YYYYMMDDhhmmss."""
+
+    PATTERN = re.compile(r"\d{14}$")
+
     def __str__(self):
-        s = str(datetime.datetime.today())
-        return s.split('.')[0].replace(' ', '').replace('-', '').replace(':', '')
+        return time.strftime("%Y%m%d%H%M%S")
 
     @classmethod
     def match(cls, s):
-        return re.match(r'\d{14}$', s)
+        return cls.PATTERN.match(s)
