@@ -367,12 +367,13 @@ def run_ours(args, c):
         fl = 2.0 * 2.0 * (T - 1) * H * H * Bl
         launch_ms = sweep_ms / 2.0 if sweep_ms else float("nan")
         ach = fl / (launch_ms * 1e-3) / 1e12
-        roof = {"kernel": "sweep_kernel (recurrent forward/BPTT sweeps, 2 launches/step)", "bound": "tensor",
+        roof = {"kernel": "sweep_cluster_kernel_v3 / sweep_kernel (recurrent forward + BPTT sweeps, 2 launches/step)", "bound": "tensor",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": ncu_traffic("sweep_kernel") if (c["H"] == 512 and Bl == 32) else None,
+                "traffic": ncu_traffic("sweep_cluster_kernel_v3") if (c["H"] == 512 and Bl == 32) else None,
                 "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": sweep_ms / tot if tot else None, "dominant_phase": dom,
-                "note": "exact-fp32 FFMA recurrence, serial in t: bounded by per-step barrier latency, not by the tensor pipe"}
+                "note": "exact-fp32 FFMA2 recurrence, serial in t (T-1 dependent steps of a 32x512x512 product): bound by issue "
+                        "rate and the per-step DSMEM exchange, not by the tensor pipe; the schema's tensor peak is only a yardstick"}
 
     # ---------------------------------------------------------------- CTC kernel in isolation (HBM roofline)
     roof_ctc = None
