@@ -39,6 +39,7 @@ struct GemmTcArgs {
     const float *bias; int relu; const float *mask;
     float *partial;      // split-K partials [splits][M][N] or nullptr
     int kb_per_split;    // k-blocks per gridDim.z slice
+    int nmma;            // debug (CTCB_GEMM_MMAS): 3 = full 3xTF32, 1 = hi.hi only (plain TF32, for rate experiments)
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -174,9 +175,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
                     const uint64_t adv = (uint64_t)((k8 * 32) >> 4);   // 8 floats = 32 bytes along the swizzled row
-                    tc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                    tc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
-                    tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                    if (g.nmma >= 3) {
+                        tc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                        tc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
+                        tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                    } else {
+                        tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
+                    }
                 }
                 tc_commit(tc_smem_u32(&bars[STAGES + s]));         // slot free once these MMAs have read it
             }
@@ -436,6 +441,11 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     const int nkb = (K + TC_BK - 1) / TC_BK;
     GemmTcArgs g;
     g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.bias = bias; g.relu = relu; g.mask = mask_src;
+    {
+        static int nmma_env = -1;
+        if (nmma_env < 0) { const char *e = getenv("CTCB_GEMM_MMAS"); nmma_env = e ? atoi(e) : 3; }
+        g.nmma = nmma_env;
+    }
     g.kb_per_split = (nkb + splits - 1) / splits;
     splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
     g.partial = splits > 1 ? part : nullptr;
