@@ -32,7 +32,7 @@ struct CtcArgs {
     int is_prob;
     int64_t us, fs;
     const int32_t *labels, *loff, *Tlen;
-    int B, Tmax, K, Kp, blank, vec2;
+    int B, Tmax, K, Kp, blank, vec2, nbuf;
     float *grad, *nll;
     int32_t *skip;
     float *ws;            // alpha-tilde spill: [B][Tmax][Lpad] doubles
@@ -114,8 +114,12 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
     const int u = blockIdx.x * (blockDim.x >> 5) + wib;
     if (u >= a.B) return;
     const int K = a.K, Kp = a.Kp, blank = a.blank;
-    float *te0 = smem + (size_t)wib * 3 * TT * Kp;   // two e tiles (double buffer) ...
-    float *tg = te0 + 2 * TT * Kp;                   // ... and the occupancy tile
+    // nbuf = 2: two e tiles (the copy of tile n+1 overlaps the work on tile n; used for small batches, where one
+    // warp has an SM almost to itself); nbuf = 1: one e tile, 1/3 less shared memory -> 24 instead of 16 warps per
+    // SM, the other warps hide the copy (large batches).  Then the occupancy tile.
+    const int nbuf = a.nbuf;
+    float *te0 = smem + (size_t)wib * (nbuf + 1) * TT * Kp;
+    float *tg = te0 + nbuf * TT * Kp;
     const int T = min(a.Tlen[u], a.Tmax);
     const int lo = a.loff[u];
     const int nlab = a.loff[u + 1] - lo;
@@ -154,14 +158,15 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         // (alpha[0,0] = p_blank, alpha[1,0] = p_label0, ctc_fast.pyx:42-47) -- no special case in the loop
         if (lane == 0) ab[0] = 1.0;
         int kscale = 0;   // power of two applied to the next frame
-        issue_tile(a, base, 0, T, te0, lane);
+        if (nbuf == 2) issue_tile(a, base, 0, T, te0, lane);
         for (int tile = 0; tile < ntiles && !fail; ++tile) {
             const int t0 = tile * TT;
-            float *te = te0 + (tile & 1) * TT * Kp;
-            if (tile + 1 < ntiles) {
+            float *te = te0 + ((nbuf == 2) ? (tile & 1) : 0) * TT * Kp;
+            if (nbuf == 2 && tile + 1 < ntiles) {
                 issue_tile(a, base, t0 + TT, T, te0 + ((tile + 1) & 1) * TT * Kp, lane);
                 cp_async_wait<1>();
             } else {
+                if (nbuf == 1) issue_tile(a, base, t0, T, te, lane);
                 cp_async_wait<0>();
             }
             __syncwarp();
@@ -231,14 +236,15 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         for (int j = 0; j < P; ++j)
             if (lane * P + j == nlab) bb[j] = 1.0;
         int kscale = 0;
-        issue_tile(a, base, (ntiles - 1) * TT, T, te0 + ((ntiles - 1) & 1) * TT * Kp, lane);
+        if (nbuf == 2) issue_tile(a, base, (ntiles - 1) * TT, T, te0 + ((ntiles - 1) & 1) * TT * Kp, lane);
         for (int tile = ntiles - 1; tile >= 0 && !fail; --tile) {
             const int t0 = tile * TT;
-            float *te = te0 + (tile & 1) * TT * Kp;
-            if (tile > 0) {
+            float *te = te0 + ((nbuf == 2) ? (tile & 1) : 0) * TT * Kp;
+            if (nbuf == 2 && tile > 0) {
                 issue_tile(a, base, t0 - TT, T, te0 + ((tile - 1) & 1) * TT * Kp, lane);
                 cp_async_wait<1>();
             } else {
+                if (nbuf == 1) issue_tile(a, base, t0, T, te, lane);
                 cp_async_wait<0>();
             }
             __syncwarp();
@@ -450,7 +456,9 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     a.grad = grad_out; a.nll = nll_out; a.skip = skip_out;
     a.ws = (float *)workspace; a.ws_utt = (int64_t)Tmax * 64 * P;
 
-    const size_t per_warp = (size_t)3 * TT * a.Kp * sizeof(float);
+    // many utterances: favour occupancy (one e tile); few: favour the latency of each warp (double-buffered tiles)
+    a.nbuf = (B >= 16 * num_sms()) ? 1 : 2;
+    const size_t per_warp = (size_t)(a.nbuf + 1) * TT * a.Kp * sizeof(float);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
     // small batches (the training step): spread the utterances over the SMs instead of packing 8 per CTA --
