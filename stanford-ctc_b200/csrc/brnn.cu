@@ -91,6 +91,12 @@ struct ctcb_brnn {
     int nlayers;        // N + 1 affine maps
     int tl;             // temporal layer or 0
     int sizes[66];      // [D, H.., K]
+    // weight/bias gradients of the layers at and above the temporal layer depend only on their delta, so they
+    // run on a side stream next to the (latency-bound, 112-SM) BPTT sweep; created on first use
+    cudaStream_t side;
+    cudaEvent_t ev_delta[66];
+    cudaEvent_t ev_side;
+    bool side_ready;
 };
 
 static int valid_cfg(const ctcb_brnn_config *c) {
@@ -155,7 +161,9 @@ extern "C" int64_t ctcb_brnn_param_count(const ctcb_brnn_config *cfg) {
 namespace {
 struct WsLayout {
     size_t X[66];       // X[1..N] activations, X[N+1] logits
-    size_t For, Back, dFor, dBack, dA, dB;
+    size_t For, Back, dFor, dBack;
+    size_t D[67];       // D[j]: gradient w.r.t. the output of affine map j (1..N+1)
+    size_t gemm2, colsum2;
     size_t ctc, gemm, colsum, scratch, counters, lens_dummy;
     size_t total;
 };
@@ -176,8 +184,7 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
         w.dBack = take(R * H * sizeof(float));
     }
     const size_t wide = (size_t)(H > K ? H : K);
-    w.dA = take(R * wide * sizeof(float));
-    w.dB = take(R * wide * sizeof(float));
+    for (int j = 1; j <= N + 1; ++j) w.D[j] = take(R * wide * sizeof(float));
     w.ctc = take(ctcb_ctc_workspace_bytes(c->maxB, c->maxT, c->maxLabels));
     size_t g = 0;
     const int Rint = (int)((R > 0x7fffffff) ? 0x7fffffff : R);
@@ -189,7 +196,9 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
     }
     need(H, H, Rint);                            // recurrent weight gradients
     w.gemm = take(g);
+    w.gemm2 = take(g);
     w.colsum = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
+    w.colsum2 = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
     w.scratch = take(8192);
     w.counters = take(sizeof(unsigned int) * 1024);
     w.total = off;
@@ -216,11 +225,29 @@ extern "C" int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out) {
     h->nlayers = cfg->numLayers + 1;
     h->tl = eff_tl(cfg);
     layer_sizes(cfg, h->sizes);
+    h->side = nullptr;
+    h->side_ready = false;
     *out = h;
     return CTCB_OK;
 }
 
-extern "C" void ctcb_brnn_destroy(ctcb_brnn *h) { delete h; }
+extern "C" void ctcb_brnn_destroy(ctcb_brnn *h) {
+    if (h && h->side_ready) {
+        cudaStreamDestroy(h->side);
+        for (int i = 0; i < 66; ++i) cudaEventDestroy(h->ev_delta[i]);
+        cudaEventDestroy(h->ev_side);
+    }
+    delete h;
+}
+
+static int ensure_side_stream(ctcb_brnn *h) {
+    if (h->side_ready) return CTCB_OK;
+    CTCB_CUDA_CHECK(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    for (int i = 0; i < 66; ++i) CTCB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_delta[i], cudaEventDisableTiming));
+    CTCB_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_side, cudaEventDisableTiming));
+    h->side_ready = true;
+    return CTCB_OK;
+}
 
 #define TRY(expr)                    \
     do {                             \
@@ -274,7 +301,7 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     float *For = (float *)(ws + w.For), *Back = (float *)(ws + w.Back);
     float *dFor = (float *)(ws + w.dFor), *dBack = (float *)(ws + w.dBack);
     void *gws = ws + w.gemm;
-    const size_t gws_bytes = w.colsum - w.gemm;
+    const size_t gws_bytes = w.gemm2 - w.gemm;
     unsigned int *counters = (unsigned int *)(ws + w.counters);
     const int iWtf = 2 * (N + 1), iWtb = 2 * (N + 1) + 2;
 
@@ -306,11 +333,11 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     if (!train) return CTCB_OK;
 
     // ---------------------------------------------------------------- CTC (brnnet.py:161-175)
-    float *dcur = (float *)(ws + w.dA), *doth = (float *)(ws + w.dB);
+    auto dbuf = [&](int j) -> float * { return (float *)(ws + w.D[j]); };
     {
     ProfScope ps("ctc", st);
     TRY(ctcb_ctc_loss_grad_f32(logits, 0, (int64_t)K, (int64_t)B * K, labels, label_off, T_per_utt, B, Tmax, K,
-                               c.maxLabels, 0, dcur, cost_out, skip_out, ws + w.ctc, w.gemm - w.ctc, st));
+                               c.maxLabels, 0, dbuf(N + 1), cost_out, skip_out, ws + w.ctc, w.gemm - w.ctc, st));
     }
 
     if (stats_out) {
@@ -319,26 +346,38 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     }
 
     // ---------------------------------------------------------------- backward (brnnet.py:188-243)
+    const bool overlap = (tl > 0);     // layers i >= tl: dW/db on the side stream, delta chain + BPTT on the main one
+    if (overlap) TRY(ensure_side_stream(h));
+    void *gws2 = ws + w.gemm2;
+    const size_t gws2_bytes = w.colsum - w.gemm2;
     for (int i = N; i >= 0; --i) {
         const float *Xi = (i == 0) ? feats : Xbuf(i);
         const int n_out = sz[i + 1], n_in = sz[i];
+        float *dcur = dbuf(i + 1);
+        const bool on_side = overlap && i >= tl;
+        cudaStream_t sw = on_side ? h->side : st;
+        if (on_side) {     // dcur is complete on the main stream here
+            CTCB_CUDA_CHECK(cudaEventRecord(h->ev_delta[i], st));
+            CTCB_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_delta[i], 0));
+        }
         // dW = delta^T . X_i   (brnnet.py:196)
         {
-        ProfScope ps("gemm_dw", st);
+        ProfScope ps("gemm_dw", sw);
         TRY(ctcb_gemm_f32(1, 0, n_out, n_in, (int)R, 1.f, dcur, n_out, Xi, n_in, 0.f, G(2 * i), n_in, nullptr, 0,
-                          nullptr, gws, gws_bytes, st));
+                          nullptr, on_side ? gws2 : gws, on_side ? gws2_bytes : gws_bytes, sw));
         }
         // db = row sums of delta   (brnnet.py:200)
         {
-            ProfScope ps("colsum", st);
+            ProfScope ps("colsum", sw);
             const int nblk = (int)((R + CS_ROWS - 1) / CS_ROWS);
-            float *part = (float *)(ws + w.colsum);
-            colsum_stage1<<<dim3((n_out + 31) / 32, nblk), dim3(32, 8), 0, st>>>(dcur, R, n_out, part);
+            float *part = (float *)(ws + (on_side ? w.colsum2 : w.colsum));
+            colsum_stage1<<<dim3((n_out + 31) / 32, nblk), dim3(32, 8), 0, sw>>>(dcur, R, n_out, part);
             CTCB_LAUNCH_CHECK();
-            colsum_stage2<<<(n_out + 127) / 128, 128, 0, st>>>(part, nblk, n_out, G(2 * i + 1));
+            colsum_stage2<<<(n_out + 127) / 128, 128, 0, sw>>>(part, nblk, n_out, G(2 * i + 1));
             CTCB_LAUNCH_CHECK();
         }
         if (i > 0) {
+            float *doth = dbuf(i);
             // delta <- delta . W, with the ReLU mask sign(hActs[i]) fused (brnnet.py:203-204,235-237)
             const float *mask = (i != tl) ? Xi : nullptr;
             {
@@ -352,21 +391,30 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
                 TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), P(iWtb), dFor, dBack, For, Back, c.maxAct,
                               counters, st));
                 }
-                ProfScope ps("gemm_dw_rec", st);
+                // recurrent weight gradients (brnnet.py:227-230): independent of the rest of the backward pass,
+                // so they go to the side stream as well
+                CTCB_CUDA_CHECK(cudaEventRecord(h->ev_delta[65], st));
+                CTCB_CUDA_CHECK(cudaStreamWaitEvent(h->side, h->ev_delta[65], 0));
+                {
+                ProfScope ps("gemm_dw_rec", h->side);
                 if (Tmax > 1) {
                     const int64_t Rm = R - B;
                     TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dFor + (int64_t)B * H, H, For, H, 0.f, G(iWtf), H,
-                                      nullptr, 0, nullptr, gws, gws_bytes, st));
+                                      nullptr, 0, nullptr, gws2, gws2_bytes, h->side));
                     TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dBack, H, Back + (int64_t)B * H, H, 0.f, G(iWtb), H,
-                                      nullptr, 0, nullptr, gws, gws_bytes, st));
+                                      nullptr, 0, nullptr, gws2, gws2_bytes, h->side));
                 } else {
-                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf), 0, sizeof(float) * H * H, st));
-                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb), 0, sizeof(float) * H * H, st));
+                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf), 0, sizeof(float) * H * H, h->side));
+                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb), 0, sizeof(float) * H * H, h->side));
+                }
                 }
                 TRY(run_add2(dFor, dBack, doth, R * H, st));
             }
-            float *t = dcur; dcur = doth; doth = t;
         }
+    }
+    if (overlap) {     // join: every gradient tensor is complete on the caller's stream from here on
+        CTCB_CUDA_CHECK(cudaEventRecord(h->ev_side, h->side));
+        CTCB_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_side, 0));
     }
     if (tl) {   // the `dummy` biases never receive gradient
         CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf + 1), 0, sizeof(float), st));

@@ -351,7 +351,10 @@ static int tc_pick_bn(int M, int N) {
     if (force < 0) { const char *e = getenv("CTCB_GEMM_BN"); force = e ? atoi(e) : 0; }
     if (force == 64 || force == 128 || force == 256) return force;
     if (N <= 64) return 64;
-    return 128;    // 256-wide tiles (2 stages only) measured slower: 0.074 vs 0.061 ms at 6400x512x512
+    // measured (tools/gemm_rate.py): 256-wide tiles win once they still fill >= 2 waves of CTAs (16384x2048x2048:
+    // 192 vs 163 TFLOP/s fp32-equivalent) and lose on small problems (6400x512x512: 0.062 vs 0.048 ms)
+    if (N >= 256 && (int64_t)((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= 2 * num_sms()) return 256;
+    return 128;
 }
 
 static int tc_choose_splits(int M, int N, int K, int BN) {
