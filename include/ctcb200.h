@@ -67,6 +67,20 @@ int ctcb_ctc_best_path_f32(const float *acts, int64_t utt_stride, int64_t frame_
                            int drop_swbd_noise, int32_t *hyp_out, int32_t *align_out,
                            int32_t *hyp_len_out, void *stream);
 
+/* ---- blank-forced CTC (replaces ctc_fast_blankforce.ctc_loss, ctc-loss/ctc_fast_blankforce.pyx:13-113) ----
+ * Same buffers as ctcb_ctc_loss_grad_f32, but `seq` already contains the blanks (:24-26): utterance u has
+ * seq_off[u+1]-seq_off[u] trellis states (at most 1024), moves s->s and s->s+1 only, one start and one end
+ * state, no window; state 0 is propagated with row 0 of the probabilities (:49).  grad_out must not alias
+ * acts.  workspace: ctcb_ctc_blankforce_workspace_bytes(B, Tmax, max_states) bytes (the alpha trellis).
+ * The best path of that module (:115-142) is ctcb_ctc_best_path_f32 with drop_swbd_noise=0; its align
+ * output is simply not used. */
+size_t ctcb_ctc_blankforce_workspace_bytes(int B, int Tmax, int max_states);
+int ctcb_ctc_blankforce_loss_grad_f32(const float *acts, int is_prob, int64_t utt_stride, int64_t frame_stride,
+                                      const int32_t *seq, const int32_t *seq_off, const int32_t *T_per_utt,
+                                      int B, int Tmax, int K, int max_states,
+                                      float *grad_out, float *nll_out, int32_t *skip_out,
+                                      void *workspace, size_t ws_bytes, void *stream);
+
 /* ---- dense fp32 contraction (replaces cudamat cm.dot call sites brnnet.py:140,196,204,227-230) ----
  * Row-major C[M x N] = alpha * op(A) * op(B) + beta * C, op(X) = X or X^T per transA/transB.
  * A is M x K (or K x M if transA), leading dimensions in elements.
@@ -91,12 +105,16 @@ typedef struct ctcb_brnn_config {
     int32_t maxLabels;     /* longest label sequence */
     float reg;             /* L2 coefficient (brnnet.py:11,177-183,197-198,244-247) */
     float maxAct;          /* clip of the temporal layer, 20.0 (brnnet.py:32) */
+    int32_t unidirectional; /* 0: nnets/brnnet.py (Wtf and Wtb, output For+Back).  1: nnets/rnnet.py:91-191 -- one
+                             * recurrent matrix, forward in time only, stack = [...layers, [Wt, dummy]] (rnnet.py:57-65).
+                             * temporalLayer <= 0 with either value is the plain DNN of nnets/nnet.py:57-113. */
 } ctcb_brnn_config;
 
 typedef struct ctcb_brnn ctcb_brnn; /* opaque; owns no device memory */
 
 /* Flat parameter vector layout: the reference's `stack` order (brnnet.py:38-41,66-72):
- * [W1,b1] ... [W_{N+1},b_{N+1}] [Wtf,dummy] [Wtb,dummy]; W row-major (out x in), dummy = 1 float. */
+ * [W1,b1] ... [W_{N+1},b_{N+1}] [Wtf,dummy] [Wtb,dummy]; W row-major (out x in), dummy = 1 float.
+ * unidirectional: [W1,b1] ... [W_{N+1},b_{N+1}] [Wt,dummy]. */
 int64_t ctcb_brnn_param_count(const ctcb_brnn_config *cfg);
 int ctcb_brnn_num_tensors(const ctcb_brnn_config *cfg);                    /* 2 * len(stack) */
 int ctcb_brnn_tensor_info(const ctcb_brnn_config *cfg, int idx, int64_t *offset, int32_t *rows, int32_t *cols);
@@ -130,6 +148,8 @@ int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_p
  * All arrays time-major [T][B][H] fp32.  mode 0: outF[t] = clip(pre[t] + outF[t-1].Wf^T, 0, maxAct),
  * outB mirrored in time with Wb; utterance u is zero beyond T_per_utt[u].
  * mode 1: outF[t] = within(actF[t]) * (pre[t] + outF[t+1].Wf), outB mirrored.
+ * Wb == NULL (with outB/actB ignored) runs the forward-in-time direction alone: the uni-directional layer of
+ * nnets/rnnet.py:112-116 [mode 0] and :162-177 [mode 1].
  * scratch: >= 4096 bytes of device memory (error flag + diagnostics). */
 int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
                         const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,

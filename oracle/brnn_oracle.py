@@ -41,7 +41,7 @@ class NNet:
 
     def __init__(self, inputDim, outputDim, layerSize, numLayers, maxBatch, train=True,
                  temporalLayer=-1, reg=0.0, dtype=np.float64, allow_top_temporal=False,
-                 round_f32=True):
+                 round_f32=True, unidirectional=False):
         self.outputDim, self.inputDim = outputDim, inputDim
         self.layerSize, self.numLayers = layerSize, numLayers
         self.layerSizes = [layerSize] * numLayers
@@ -55,6 +55,10 @@ class NNet:
         hi = numLayers + 1 if allow_top_temporal else numLayers
         self.temporalLayer = -1 if (temporalLayer <= 0 or temporalLayer >= hi) else temporalLayer
         self.maxAct = 20.0
+        # unidirectional: the restatement of nnets/rnnet.py:8-191 (one recurrent matrix, forward in time only);
+        # with temporalLayer=-1 either setting is nnets/nnet.py:57-113 (same loops without the temporal branch)
+        self.unidirectional = unidirectional
+        self.nrec = 0 if self.temporalLayer <= 0 else (1 if unidirectional else 2)
 
     def initParams(self):
         # brnnet.py:38-41 then :66-70 -- identical draw order from the global np.random stream
@@ -65,9 +69,10 @@ class NNet:
         if self.temporalLayer > 0:
             scale = np.sqrt(6) / np.sqrt(self.layerSize * 2)
             wtf = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
-            wtb = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
             self.stack.append([wtf, np.zeros((1, 1))])
-            self.stack.append([wtb, np.zeros((1, 1))])
+            if not self.unidirectional:                                   # rnnet.py:57-61: a single wt
+                wtb = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
+                self.stack.append([wtb, np.zeros((1, 1))])
         # cudamat stores float32 (cm.CUDAMatrix(w) converts): round the float64 draws once
         self.stack = [[w.astype(np.float32).astype(self.dtype), b.astype(self.dtype)] for w, b in self.stack]
         self.grad = [[np.zeros_like(w), np.zeros_like(b)] for w, b in self.stack]
@@ -79,13 +84,20 @@ class NNet:
         """brnnet.py:136-168.  Returns (hActs list, For, Back, probs) with probs float32-rounded."""
         dt = self.dtype
         T = data.shape[1]
-        stack = self.stack[:-2] if self.temporalLayer > 0 else self.stack
+        stack = self.stack[:-self.nrec] if self.nrec else self.stack
         hActs = [np.asarray(data, dtype=dt)]
         For = Back = None
         i = 1
         for w, b in stack:
             h = w.dot(hActs[i - 1]) + b                                    # :140-141
-            if i == self.temporalLayer:                                   # :143-153
+            if i == self.temporalLayer and self.unidirectional:           # rnnet.py:112-116
+                wt = self.stack[-1][0]
+                For = h.copy()
+                For[:, 0] = np.clip(For[:, 0], 0.0, self.maxAct)
+                for t in range(1, T):
+                    For[:, t] = np.clip(For[:, t] + wt.dot(For[:, t - 1]), 0.0, self.maxAct)
+                h = For
+            elif i == self.temporalLayer:                                 # :143-153
                 wtf, wtb = self.stack[-2][0], self.stack[-1][0]
                 For, Back = h.copy(), h.copy()
                 For[:, 0] = np.clip(For[:, 0], 0.0, self.maxAct)
@@ -120,7 +132,10 @@ class NNet:
                 cost = cost + rc
         if skip:
             return cost, self.grad, skip                                  # :185-186
-        if self.temporalLayer > 0:
+        if self.nrec == 1:
+            stack, grad = self.stack[:-1], self.grad[:-1]
+            wtf = self.stack[-1][0]
+        elif self.nrec == 2:
             stack, grad = self.stack[:-2], self.grad[:-2]
             wtf, wtb = self.stack[-2][0], self.stack[-1][0]
         else:
@@ -135,7 +150,16 @@ class NNet:
             deltasOut = None
             if i > 0:
                 deltasOut = w.T.dot(deltasIn)                             # :203-204
-            if i == self.temporalLayer:                                   # :207-233
+            if i == self.temporalLayer and self.unidirectional:           # rnnet.py:162-177
+                mF = ((For > 0.0) & (For < self.maxAct)).astype(dt)
+                dFor = deltasOut.copy()
+                dFor[:, T - 1] *= mF[:, T - 1]
+                for t in range(T - 1, 0, -1):
+                    dFor[:, t - 1] += wtf.T.dot(dFor[:, t])
+                    dFor[:, t - 1] *= mF[:, t - 1]
+                self.grad[-1][0] = dFor[:, 1:T].dot(For[:, 0:T - 1].T)    # rnnet.py:173-174 (deltaTemp = delta shifted by one)
+                deltasOut = dFor
+            elif i == self.temporalLayer:                                 # :207-233
                 mF = ((For > 0.0) & (For < self.maxAct)).astype(dt)       # within(0,maxAct)
                 mB = ((Back > 0.0) & (Back < self.maxAct)).astype(dt)
                 dFor, dBack = deltasOut.copy(), deltasOut.copy()
@@ -153,7 +177,7 @@ class NNet:
                 deltasOut = deltasOut * (hActs[i] > 0.0)
             deltasIn = deltasOut
             i -= 1
-        if self.reg > 0 and self.temporalLayer > 0:                       # :244-247
+        if self.reg > 0 and self.nrec == 2:                               # :244-247
             self.grad[-2][0] = self.grad[-2][0] + self.reg * wtf
             self.grad[-1][0] = self.grad[-1][0] + self.reg * wtb
         return cost, self.grad, skip

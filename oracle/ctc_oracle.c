@@ -143,3 +143,96 @@ int ctc_oracle_best_path(const double *probs, int K, int T, int blank, int *hyp,
     }
     return n;
 }
+
+/*
+ * Blank-forced variant: /root/reference/ctc_fast/ctc-loss/ctc_fast_blankforce.pyx:13-113.
+ * `seq` already contains the blanks (:24-26): L = seqLen states, transitions s -> s and s -> s+1
+ * only (:51-52), a single start state (:43) and a single end state (:64); every state enters the
+ * per-frame normaliser (:55-59), so -llForward is the log of the total mass of ALL states at T-1.
+ * Quirk kept: state 0 is propagated with params[0,t] -- row index s, not seq[s] (:49).
+ * Same skip rule: a zero normaliser raises ZeroDivisionError in the reference (:108-110).
+ */
+int ctc_oracle_loss_blankforce(const double *params, int K, int T, const int *seq, int seqLen,
+                               double *grad, double *nll)
+{
+    int L = seqLen;
+    double *alphas = (double *)calloc((size_t)L * T, sizeof(double));
+    double *betas = (double *)calloc((size_t)L * T, sizeof(double));
+    double *ab = (double *)malloc((size_t)L * T * sizeof(double));
+    double *absum = (double *)malloc((size_t)T * sizeof(double));
+    double c, llForward, llBackward, tmp;
+    int t, s, skip = 0;
+    memset(grad, 0, (size_t)K * T * sizeof(double));
+
+    A(0, 0) = 1.0;                                             /* :43 */
+    llForward = log(P(seq[0], 0));                             /* :44 */
+    for (t = 1; t < T && !skip; ++t) {                         /* :45-59 */
+        for (s = 0; s < L; ++s) {
+            if (s == 0) A(s, t) = A(s, t - 1) * P(s, t);
+            else A(s, t) = (A(s, t - 1) + A(s - 1, t - 1)) * P(seq[s], t);
+        }
+        c = 0.0;
+        for (s = 0; s < L; ++s) c += A(s, t);
+        if (c == 0.0) { skip = 1; break; }
+        for (s = 0; s < L; ++s) A(s, t) = A(s, t) / c;
+        llForward += log(c);
+    }
+    if (!skip) {
+        B(L - 1, T - 1) = 1.0;                                 /* :64 */
+        llBackward = log(P(seq[L - 1], T - 1));
+        for (t = T - 2; t >= 0 && !skip; --t) {                /* :66-82 */
+            for (s = L - 1; s >= 0; --s) {
+                if (s == L - 1) B(s, t) = B(s, t + 1) * P(seq[s], t);
+                else B(s, t) = (B(s, t + 1) + B(s + 1, t + 1)) * P(seq[s], t);
+            }
+            c = 0.0;
+            for (s = 0; s < L; ++s) c += B(s, t);
+            if (c == 0.0) { skip = 1; break; }
+            for (s = 0; s < L; ++s) B(s, t) = B(s, t) / c;
+            llBackward += log(c);
+        }
+        (void)llBackward;
+    }
+    if (!skip) {
+        for (t = 0; t < T; ++t)                                /* :85-87 */
+            for (s = 0; s < L; ++s) AB(s, t) = A(s, t) * B(s, t);
+        for (s = 0; s < L && !skip; ++s)                       /* :88-92 */
+            for (t = 0; t < T; ++t) {
+                G(seq[s], t) += AB(s, t);
+                if (AB(s, t) != 0) {
+                    if (P(seq[s], t) == 0.0) { skip = 1; break; }
+                    AB(s, t) = AB(s, t) / P(seq[s], t);
+                }
+            }
+    }
+    if (!skip) {
+        for (t = 0; t < T; ++t) {                              /* :94-97 */
+            absum[t] = 0;
+            for (s = 0; s < L; ++s) absum[t] += AB(s, t);
+        }
+        for (t = 0; t < T; ++t)                                /* :100-106 */
+            for (s = 0; s < K; ++s) {
+                tmp = P(s, t) * absum[t];
+                if (tmp > 0) G(s, t) = P(s, t) - G(s, t) / tmp;
+                else G(s, t) = P(s, t);
+            }
+    }
+    *nll = -llForward;
+    free(alphas); free(betas); free(ab); free(absum);
+    return skip;
+}
+
+/* ctc_fast_blankforce.pyx:115-142: argmax per frame, drop blanks and repeats (no label filter, no
+ * alignment output).  Returns the hypothesis length. */
+int ctc_oracle_best_path_blankforce(const double *probs, int K, int T, int blank, int *hyp)
+{
+    int n = 0, prev = -1, t, k;
+    for (t = 0; t < T; ++t) {
+        int b = 0;
+        for (k = 1; k < K; ++k)
+            if (probs[(size_t)k + (size_t)K * t] > probs[(size_t)b + (size_t)K * t]) b = k;
+        if (b != blank && !(t != 0 && b == prev)) hyp[n++] = b;
+        prev = b;
+    }
+    return n;
+}

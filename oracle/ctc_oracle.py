@@ -1,7 +1,7 @@
 """oracle/ctc_oracle.py -- TEST INFRASTRUCTURE ONLY.
 
 ctypes front-end of oracle/ctc_oracle.c (the float64 C restatement of
-/root/reference/ctc_fast/ctc-loss/ctc_fast.pyx:13-187) plus a loader for oracle/_ref (the
+/root/reference/ctc_fast/ctc-loss/ctc_fast.pyx:13-187 and ctc_fast_blankforce.pyx:13-142) plus a loader for oracle/_ref (the
 reference's own .pyx compiled unmodified by oracle/build_ref.py).
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
@@ -42,6 +42,12 @@ def _lib():
         _LIB.ctc_oracle_best_path.restype = ctypes.c_int
         _LIB.ctc_oracle_best_path.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                               ctypes.c_void_p, ctypes.c_void_p]
+        _LIB.ctc_oracle_loss_blankforce.restype = ctypes.c_int
+        _LIB.ctc_oracle_loss_blankforce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                                    ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        _LIB.ctc_oracle_best_path_blankforce.restype = ctypes.c_int
+        _LIB.ctc_oracle_best_path_blankforce.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                         ctypes.c_void_p]
     return _LIB
 
 
@@ -69,33 +75,68 @@ def decode_best_path(probs, blank=0):
     return hyp[:n].tolist(), align[:n].tolist()
 
 
+def ctc_loss_blankforce(params, seq):
+    """ctc_fast_blankforce.pyx:13-113 restated (oracle/ctc_oracle.c): seq already holds the blanks."""
+    if not (isinstance(params, np.ndarray) and params.dtype == np.float64 and params.ndim == 2
+            and params.flags.f_contiguous):
+        raise ValueError("ndarray is not Fortran contiguous")
+    seq = np.ascontiguousarray(seq, dtype=np.int32)
+    K, T = params.shape
+    grad = np.zeros((K, T), dtype=np.float64, order="F")
+    nll = ctypes.c_double(0.0)
+    skip = _lib().ctc_oracle_loss_blankforce(params.ctypes.data, K, T, seq.ctypes.data, seq.shape[0],
+                                             grad.ctypes.data, ctypes.addressof(nll))
+    return nll.value, grad, bool(skip)
+
+
+def decode_best_path_blankforce(probs, blank=0):
+    """ctc_fast_blankforce.pyx:115-142: returns the hypothesis only."""
+    probs = np.asfortranarray(probs, dtype=np.float64)
+    K, T = probs.shape
+    hyp = np.zeros(T, dtype=np.int32)
+    n = _lib().ctc_oracle_best_path_blankforce(probs.ctypes.data, K, T, int(blank), hyp.ctypes.data)
+    return hyp[:n].tolist()
+
+
 # ---------------------------------------------------------------------------------------------
 # oracle/_ref: the unmodified reference extension (kind "reference")
 # ---------------------------------------------------------------------------------------------
-_REF = None
+_REF = {}
 
 
-def ref_module():
-    """Import the compiled reference ctc_fast from oracle/_ref (None if it was never built)."""
-    global _REF
-    if _REF is None:
+def ref_module(name="ctc_fast"):
+    """Import a compiled reference module (ctc_fast | ctc_fast_blankforce) from oracle/_ref; None if
+    it was never built."""
+    if name not in _REF:
         import importlib.util
         import sysconfig
-        so = os.path.join(HERE, "_ref", "ctc_fast" + sysconfig.get_config_var("EXT_SUFFIX"))
+        so = os.path.join(HERE, "_ref", name + sysconfig.get_config_var("EXT_SUFFIX"))
         if not os.path.exists(so):
             return None
-        # The extension's init symbol is PyInit_ctc_fast, so it must be loaded under that name; keep it
+        # The extension's init symbol is PyInit_<name>, so it must be loaded under that name; keep it
         # OUT of sys.modules so that `import ctc_fast` still resolves to the product's drop-in module.
-        prev = sys.modules.get("ctc_fast")
-        spec = importlib.util.spec_from_file_location("ctc_fast", so)
+        prev = sys.modules.get(name)
+        spec = importlib.util.spec_from_file_location(name, so)
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         if prev is not None:
-            sys.modules["ctc_fast"] = prev
+            sys.modules[name] = prev
         else:
-            sys.modules.pop("ctc_fast", None)
-        _REF = mod
-    return _REF
+            sys.modules.pop(name, None)
+        _REF[name] = mod
+    return _REF[name]
+
+
+def ref_ctc_loss_blankforce(params, seq):
+    """The unmodified ctc_fast_blankforce.ctc_loss; failure path mapped as in ref_ctc_loss."""
+    mod = ref_module("ctc_fast_blankforce")
+    if mod is None:
+        raise RuntimeError("oracle/_ref not built (run oracle/build_ref.py where /root/reference exists)")
+    try:
+        nll, grad, skip = mod.ctc_loss(params, np.ascontiguousarray(seq, dtype=np.int32))
+        return float(nll), grad, bool(skip)
+    except (AttributeError, ZeroDivisionError, FloatingPointError):
+        return float("nan"), np.zeros(params.shape, dtype=np.float64, order="F"), True
 
 
 def ref_ctc_loss(params, seq, blank=0):

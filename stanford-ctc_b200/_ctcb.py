@@ -24,7 +24,7 @@ class BrnnConfig(ctypes.Structure):
     _fields_ = [("inputDim", ctypes.c_int32), ("outputDim", ctypes.c_int32), ("layerSize", ctypes.c_int32),
                 ("numLayers", ctypes.c_int32), ("temporalLayer", ctypes.c_int32), ("maxT", ctypes.c_int32),
                 ("maxB", ctypes.c_int32), ("maxLabels", ctypes.c_int32), ("reg", ctypes.c_float),
-                ("maxAct", ctypes.c_float)]
+                ("maxAct", ctypes.c_float), ("unidirectional", ctypes.c_int32)]
 
 
 _PROTOS = {
@@ -38,6 +38,9 @@ _PROTOS = {
                                        c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "ctcb_ctc_best_path_f32": (c_int, [c_vp, c_i64, c_i64, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp,
                                        c_vp, c_vp]),
+    "ctcb_ctc_blankforce_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
+    "ctcb_ctc_blankforce_loss_grad_f32": (c_int, [c_vp, c_int, c_i64, c_i64, c_vp, c_vp, c_vp, c_int, c_int, c_int,
+                                                  c_int, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "ctcb_gemm_workspace_bytes": (c_sz, [c_int, c_int, c_int]),
     "ctcb_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp,
                               c_i64, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),

@@ -117,7 +117,7 @@ static void layer_sizes(const ctcb_brnn_config *c, int *sizes) {
 
 extern "C" int ctcb_brnn_num_tensors(const ctcb_brnn_config *cfg) {
     if (!valid_cfg(cfg)) return 0;
-    return 2 * (cfg->numLayers + 1) + (eff_tl(cfg) ? 4 : 0);
+    return 2 * (cfg->numLayers + 1) + (eff_tl(cfg) ? (cfg->unidirectional ? 2 : 4) : 0);
 }
 
 extern "C" int ctcb_brnn_tensor_info(const ctcb_brnn_config *cfg, int idx, int64_t *offset, int32_t *rows, int32_t *cols) {
@@ -258,7 +258,8 @@ static int ensure_side_stream(ctcb_brnn *h) {
 extern "C" int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
                                    const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
                                    const float *actB, float maxAct, void *scratch, void *stream) {
-    if (!T_per_utt || !pre || !Wf || !Wb || !outF || !outB || !scratch || (mode == 1 && (!actF || !actB)))
+    if (!T_per_utt || !pre || !Wf || !outF || !scratch || (mode == 1 && !actF) ||
+        (Wb && (!outB || (mode == 1 && !actB))))
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: null pointer argument");
     if (T <= 0 || B <= 0 || H <= 0 || (mode != 0 && mode != 1))
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: bad sizes");
@@ -304,10 +305,14 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     const size_t gws_bytes = w.gemm2 - w.gemm;
     unsigned int *counters = (unsigned int *)(ws + w.counters);
     const int iWtf = 2 * (N + 1), iWtb = 2 * (N + 1) + 2;
+    const bool uni = (c.unidirectional != 0);
+    // activations of layer i as the next layer (and the weight gradients) see them: the uni-directional temporal
+    // layer's output IS the forward sweep (rnnet.py:112-116), the bi-directional one's is For + Back
+    auto Act = [&](int i) -> float * { return (uni && i == tl && tl > 0) ? For : Xbuf(i); };
 
     // ---------------------------------------------------------------- forward (brnnet.py:136-157)
     for (int i = 1; i <= N + 1; ++i) {
-        const float *in = (i == 1) ? feats : Xbuf(i - 1);
+        const float *in = (i == 1) ? feats : Act(i - 1);
         const int relu = (i <= N && i != tl) ? 1 : 0;
         {
         ProfScope ps("gemm_fwd", st);
@@ -317,11 +322,13 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
         if (i == tl) {
             {
             ProfScope ps("sweep_fwd", st);
-            TRY(run_sweep(0, Tmax, B, H, T_per_utt, Xbuf(i), P(iWtf), P(iWtb), For, Back, nullptr, nullptr,
-                          c.maxAct, counters, st));
+            TRY(run_sweep(0, Tmax, B, H, T_per_utt, Xbuf(i), P(iWtf), uni ? nullptr : P(iWtb), For, Back, nullptr,
+                          nullptr, c.maxAct, counters, st));
             }
-            ProfScope ps("elementwise", st);
-            TRY(run_add2(For, Back, Xbuf(i), R * H, st));     // brnnet.py:153
+            if (!uni) {
+                ProfScope ps("elementwise", st);
+                TRY(run_add2(For, Back, Xbuf(i), R * H, st));     // brnnet.py:153
+            }
         }
     }
     float *logits = Xbuf(N + 1);
@@ -351,9 +358,9 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     void *gws2 = ws + w.gemm2;
     const size_t gws2_bytes = w.colsum - w.gemm2;
     for (int i = N; i >= 0; --i) {
-        const float *Xi = (i == 0) ? feats : Xbuf(i);
+        const float *Xi = (i == 0) ? feats : Act(i);
         const int n_out = sz[i + 1], n_in = sz[i];
-        float *dcur = dbuf(i + 1);
+        float *dcur = (uni && tl > 0 && i + 1 == tl) ? dFor : dbuf(i + 1);   // rnnet.py:162-177: the BPTT result is the delta
         const bool on_side = overlap && i >= tl;
         cudaStream_t sw = on_side ? h->side : st;
         if (on_side) {     // dcur is complete on the main stream here
@@ -388,8 +395,8 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
             if (i == tl) {   // brnnet.py:207-233
                 {
                 ProfScope ps("sweep_bptt", st);
-                TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), P(iWtb), dFor, dBack, For, Back, c.maxAct,
-                              counters, st));
+                TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), uni ? nullptr : P(iWtb), dFor, dBack, For, Back,
+                              c.maxAct, counters, st));
                 }
                 // recurrent weight gradients (brnnet.py:227-230): independent of the rest of the backward pass,
                 // so they go to the side stream as well
@@ -401,14 +408,15 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
                     const int64_t Rm = R - B;
                     TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dFor + (int64_t)B * H, H, For, H, 0.f, G(iWtf), H,
                                       nullptr, 0, nullptr, gws2, gws2_bytes, h->side));
-                    TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dBack, H, Back + (int64_t)B * H, H, 0.f, G(iWtb), H,
-                                      nullptr, 0, nullptr, gws2, gws2_bytes, h->side));
+                    if (!uni)
+                        TRY(ctcb_gemm_f32(1, 0, H, H, (int)Rm, 1.f, dBack, H, Back + (int64_t)B * H, H, 0.f, G(iWtb), H,
+                                          nullptr, 0, nullptr, gws2, gws2_bytes, h->side));
                 } else {
                     CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf), 0, sizeof(float) * H * H, h->side));
-                    CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb), 0, sizeof(float) * H * H, h->side));
+                    if (!uni) CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb), 0, sizeof(float) * H * H, h->side));
                 }
                 }
-                TRY(run_add2(dFor, dBack, doth, R * H, st));
+                if (!uni) TRY(run_add2(dFor, dBack, doth, R * H, st));
             }
         }
     }
@@ -418,7 +426,7 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     }
     if (tl) {   // the `dummy` biases never receive gradient
         CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtf + 1), 0, sizeof(float), st));
-        CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb + 1), 0, sizeof(float), st));
+        if (!uni) CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb + 1), 0, sizeof(float), st));
     }
 
     // ---------------------------------------------------------------- L2 (brnnet.py:177-183,197-198,244-247)

@@ -42,6 +42,7 @@ struct SweepArgs {
     const float *act[2];    // mode 1: For, Back (for the within(0,maxAct) masks)
     float maxAct;
     int parts;              // utterance partitions (gridDim.y)
+    int ndir;               // 2: forward and backward direction (gridDim.z); 1: forward in time only
     unsigned int *counters; // [2 * parts], zeroed before launch
 };
 
@@ -203,18 +204,18 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     CTCB_CUDA_CHECK(cudaFuncSetAttribute(sweep_kernel<KI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CTCB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sweep_kernel<KI>, SW_THREADS, smem));
     const int capacity = per_sm * num_sms();
-    if (2 * slices > capacity)
+    if (a.ndir * slices > capacity)
         return set_error(CTCB_EINVAL, "recurrent sweep: layerSize %d needs %d co-resident CTAs, device holds %d",
-                         a.H, 2 * slices, capacity);
+                         a.H, a.ndir * slices, capacity);
     const int ntiles = (a.B + SW_NB - 1) / SW_NB;
-    int parts = capacity / (2 * slices);
+    int parts = capacity / (a.ndir * slices);
     if (parts > ntiles) parts = ntiles;
     if (parts > 500) parts = 500;   // counters region holds 1024 words
     if (parts < 1) parts = 1;
     a.parts = parts;
     a.counters += 16;     // words [0..15] are reserved for error flags
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters - 16, 0, sizeof(unsigned int) * (16 + 2 * parts), st));
-    dim3 grid(slices, parts, 2);
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters - 16, 0, sizeof(unsigned int) * (16 + a.ndir * parts), st));
+    dim3 grid(slices, parts, a.ndir);
     void *params[] = {&a};
     CTCB_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)sweep_kernel<KI>, grid, dim3(SW_THREADS), params, smem, st));
     count_launch();
@@ -233,6 +234,8 @@ int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *p
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB;
     a.maxAct = maxAct; a.counters = counters; a.parts = 1;
+    a.ndir = Wb ? 2 : 1;
+    if (!Wb) { a.W[1] = Wf; a.out[1] = outF; a.act[1] = actF; }   // never dereferenced: gridDim.z == 1
     {   // cluster/DSMEM fast path (H = 128, 256, 512); CTCB_SWEEP=barrier forces the general kernel
         static int force_barrier = -1;
         if (force_barrier < 0) {

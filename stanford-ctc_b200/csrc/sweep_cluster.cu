@@ -28,6 +28,7 @@ struct SweepClusterArgs {
     const float *act[2];
     float maxAct;
     unsigned int *err;      // [0] set to 2 if a barrier wait timed out (never a hang)
+    int ndir;               // gridDim.z: 2 = both directions, 1 = forward in time only
     int opt;                // tuning bits (CTCB_SWEEP_OPT): 1 = one polling lane per warp, 2 = HBM store after the push
 };
 
@@ -207,7 +208,7 @@ static int launch_cluster(const SweepClusterArgs &a, cudaStream_t st, bool *hand
     const int ntiles = (a.B + NB - 1) / NB;
     if (ntiles > 65535) return CTCB_OK;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(CS, ntiles, 2);
+    cfg.gridDim = dim3(CS, ntiles, a.ndir);
     cfg.blockDim = dim3(SC_THREADS);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
@@ -228,7 +229,7 @@ static int launch_cluster(const SweepClusterArgs &a, cudaStream_t st, bool *hand
     }
     if (getenv("CTCB_DEBUG")) {
         static bool once = false;
-        if (!once) { once = true; fprintf(stderr, "[ctcb] sweep v2 H=%d rpw=%d: cluster=%d, grid clusters=%d, max active clusters=%d\n", 32 * KI, RPW, CS, ntiles * 2, nclusters); }
+        if (!once) { once = true; fprintf(stderr, "[ctcb] sweep v2 H=%d rpw=%d: cluster=%d, grid clusters=%d, max active clusters=%d\n", 32 * KI, RPW, CS, ntiles * a.ndir, nclusters); }
     }
     CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, (sweep_cluster_kernel<KI, RPW>), a));
     count_launch();
@@ -400,7 +401,7 @@ template <int KI, int NB>
 static int launch_cluster_v3_nb(const SweepClusterArgs &a, int ntiles, cudaStream_t st) {
     constexpr int CS = KI / 2;
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(CS, ntiles, 2);
+    cfg.gridDim = dim3(CS, ntiles, a.ndir);
     cfg.blockDim = dim3(512);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
@@ -440,7 +441,7 @@ static int launch_cluster_v3(const SweepClusterArgs &a, cudaStream_t st, bool *h
     if (nb_env < 0) { const char *e = getenv("CTCB_SWEEP_NB"); nb_env = e ? atoi(e) : 0; }
     int nb = 0;
     for (int c = 4; c <= 8; ++c)
-        if (2 * ((a.B + c - 1) / c) <= max_clusters) { nb = c; break; }
+        if (a.ndir * ((a.B + c - 1) / c) <= max_clusters) { nb = c; break; }
     if (nb_env >= 4 && nb_env <= 8) nb = nb_env;
     if (nb == 0) return CTCB_OK;          // would need a second wave of clusters: the general kernel is faster
     const int ntiles = (a.B + nb - 1) / nb;
@@ -467,6 +468,8 @@ int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const 
     SweepClusterArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB; a.maxAct = maxAct; a.err = err;
+    a.ndir = Wb ? 2 : 1;
+    if (!Wb) { a.W[1] = Wf; a.out[1] = outF; a.act[1] = actF; }
     {
         static int opt = -1;
         if (opt < 0) { const char *e = getenv("CTCB_SWEEP_OPT"); opt = e ? atoi(e) : 0; }

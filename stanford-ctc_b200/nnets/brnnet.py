@@ -101,7 +101,7 @@ class NNet:
 
     def __init__(self, inputDim, outputDim, layerSize, numLayers, maxBatch,
                  train=True, temporalLayer=-1, reg=0.0, maxUtts=1, maxLabels=None,
-                 allowTopTemporal=False, device=None):
+                 allowTopTemporal=False, device=None, unidirectional=False):
         torch = _ctcb.require_cuda()
         self._torch = torch
         self.dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
@@ -127,8 +127,10 @@ class NNet:
             self.temporalLayer = temporalLayer
         self.maxAct = 20.0
 
+        # unidirectional: the single forward-in-time recurrence of nnets/rnnet.py (used by nnets.rnnet.NNet)
+        self.unidirectional = bool(unidirectional)
         self._cfg = BrnnConfig(inputDim, outputDim, layerSize, numLayers, max(self.temporalLayer, 0), maxBatch,
-                               maxUtts, self.maxLabels, float(reg), float(self.maxAct))
+                               maxUtts, self.maxLabels, float(reg), float(self.maxAct), int(self.unidirectional))
         self._h = ctypes.c_void_p()
         check(lib.ctcb_brnn_create(ctypes.byref(self._cfg), ctypes.byref(self._h)))
         self.stack = None
@@ -162,9 +164,10 @@ class NNet:
         if self.temporalLayer > 0:
             scale = np.sqrt(6) / np.sqrt(self.layerSize * 2)
             wtf = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
-            wtb = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
             host.append([wtf, np.zeros((1, 1))])
-            host.append([wtb, np.zeros((1, 1))])
+            if not self.unidirectional:            # rnnet.py:57-61 draws a single recurrent matrix
+                wtb = 2 * scale * np.random.rand(self.layerSize, self.layerSize) - scale
+                host.append([wtb, np.zeros((1, 1))])
 
         self.nparams = int(lib.ctcb_brnn_param_count(ctypes.byref(self._cfg)))
         self.params = torch.zeros(self.nparams, dtype=torch.float32, device=self.dev)

@@ -27,6 +27,18 @@ def golden_brnn():
 
 
 @pytest.fixture(scope="session")
+def golden_bf():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "blankforce_cases.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_rnn():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "rnn_cases.npz"))
+
+
+@pytest.fixture(scope="session")
 def cuda():
     import torch
     if not torch.cuda.is_available():

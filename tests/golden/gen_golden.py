@@ -1,7 +1,7 @@
 """Generates tests/golden/*.npz by running the REFERENCE ITSELF in the authoring container:
   * CTC cases through oracle/_ref = the unmodified /root/reference/ctc_fast/ctc-loss/ctc_fast.pyx
-    (compiled by oracle/build_ref.py), fed probs.astype(float64) in Fortran order as
-    brnnet.py:175 does;
+    and ctc_fast_blankforce.pyx (compiled by oracle/build_ref.py), fed probs.astype(float64) in Fortran
+    order as brnnet.py:175 does;
   * BRNN cases through oracle/brnn_oracle.py (float64 restatement of brnnet.py; the cudamat half of
     the reference is not runnable here) with the CTC inside it again served by oracle/_ref.
 
@@ -35,6 +35,19 @@ def main():
         out[name + "/gradnorm"] = np.float64(np.linalg.norm(grad))
         print("%-36s nll=%.9f |g|=%.9f skip=%s" % (name, nll, np.linalg.norm(grad), skip))
     np.savez_compressed(os.path.join(HERE, "ctc_cases.npz"), **out)
+
+    # blank-forced CTC through the unmodified ctc_fast_blankforce.pyx
+    out = {}
+    for name in recipes.ALL_BF:
+        probs, seq = recipes.bf_case(name)
+        nll, grad, skip = ctc_oracle.ref_ctc_loss_blankforce(np.asfortranarray(probs.astype(np.float64)), seq)
+        out[name + "/nll"] = np.float64(nll)
+        out[name + "/skip"] = np.bool_(skip)
+        st = recipes.golden_stride(*probs.shape)
+        out[name + "/grad"] = grad[:, ::st].astype(np.float32)
+        out[name + "/gradnorm"] = np.float64(np.linalg.norm(grad))
+        print("%-36s nll=%.9f |g|=%.9f skip=%s" % (name, nll, np.linalg.norm(grad), skip))
+    np.savez_compressed(os.path.join(HERE, "blankforce_cases.npz"), **out)
 
     out = {}
     # (1) the reference's own CPU BRNN self-test recipe
@@ -73,6 +86,22 @@ def main():
         out["ragged/dw%d" % i] = dw; out["ragged/db%d" % i] = db
     print("ragged costs", costs, "clip hits", out["ragged/clip_hits"], "regcost", nn.regcost)
     np.savez_compressed(os.path.join(HERE, "brnn_cases.npz"), **out)
+
+    # (3) the uni-directional net (nnets/rnnet.py) and the feed-forward net (nnets/nnet.py) on a ragged minibatch
+    out = {}
+    datas, labelss = recipes.rnn_variant_batch()
+    for tag, _ in recipes.RNN_VARIANTS:
+        nn = recipes.rnn_variant_net(brnn_oracle.NNet, tag, dtype=np.float64)
+        recipes.rnn_variant_perturb(nn.stack, tag)
+        if tag == "uni":
+            out["uni/clip_hits"] = np.int64(np.sum(nn.forward(datas[1])[1] >= 20.0))
+        costs, grad, skips = nn.costAndGradBatch(datas, labelss)
+        out[tag + "/costs"] = costs; out[tag + "/skips"] = skips
+        for i, ((w, b), (dw, db)) in enumerate(zip(nn.stack, grad)):
+            out[tag + "/w%d" % i] = w.astype(np.float32); out[tag + "/b%d" % i] = b.astype(np.float32)
+            out[tag + "/dw%d" % i] = dw; out[tag + "/db%d" % i] = db
+        print(tag, "costs", costs, "clip hits", out.get("uni/clip_hits"))
+    np.savez_compressed(os.path.join(HERE, "rnn_cases.npz"), **out)
 
 
 if __name__ == "__main__":

@@ -99,3 +99,58 @@ def synth_batch(inputDim, outputDim, lens, nlabs, seed=33):
     datas = [rng.randn(inputDim, T).astype(np.float32) for T in lens]
     labels = [(1 + np.floor(rng.rand(n) * (outputDim - 1))).astype(np.int32) for n in nlabs]
     return datas, labels
+
+
+# ---- blank-forced CTC (ctc_fast_blankforce.pyx): the sequence carries its blanks ---------------------
+BF_CASES = {
+    # name: (T, K, number of non-blank labels)
+    "bf_c1": (200, 62, 30),
+    "bf_small": (10, 6, 3),
+    "bf_wsj": (800, 32, 100),
+    "bf_long": (1500, 35, 300),
+    "bf_T_less_than_L": (8, 10, 6),          # no exception in the reference: absum == 0 -> grad = probs
+    "bf_no_leading_blank": (50, 20, 10),     # seq[0] != 0 exercises the row-0 quirk (:49)
+    "bf_one_state": (7, 5, 0),
+    "bf_peaked": (400, 40, 60),
+}
+
+
+def bf_case(name):
+    """Returns (probs float32 K x T, seq int32 with blanks interleaved: 0 l1 0 l2 ... 0)."""
+    T, K, nlab = BF_CASES[name]
+    logits, lab = synth_ctc(T, K, nlab, seed=77)
+    if name == "bf_peaked":
+        logits = logits * 4.0
+    seq = np.zeros(2 * nlab + 1, dtype=np.int32)
+    seq[1::2] = lab
+    if name == "bf_no_leading_blank":
+        seq = seq[1:].copy()
+    return softmax_cols(logits).astype(np.float32), seq
+
+
+ALL_BF = list(BF_CASES)
+
+
+RNN_VARIANTS = (("uni", dict(temporalLayer=2, unidirectional=True)), ("dnn", dict(temporalLayer=-1)))
+
+
+def rnn_variant_batch():
+    return synth_batch(13, 11, [30, 41, 12, 41], [7, 11, 3, 15], seed=11)
+
+
+def rnn_variant_net(cls, tag, **extra):
+    """The uni-directional (nnets/rnnet.py) / feed-forward (nnets/nnet.py) golden nets: D=13, K=11, H=64, N=3."""
+    kw = dict(RNN_VARIANTS)[tag]
+    np.random.seed(9)
+    nn = cls(13, 11, 64, 3, 41, **dict(kw, **extra))
+    nn.initParams()
+    return nn
+
+
+def rnn_variant_perturb(stack, tag):
+    """Host-side edits of the freshly initialised stack (list of [w, b] arrays) that the golden nets carry."""
+    for w, b in stack[:3]:
+        b += 0.05
+    if tag == "uni":
+        stack[1][1] += 4.0          # some units reach the 20.0 clip (rnnet.py:32,113-116)
+        stack[-1][0] *= 1.2

@@ -27,7 +27,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_header_cites_reference_interfaces():
     src = open(os.path.join(ROOT, "include", "ctcb200.h")).read()
-    for cite in ("ctc_fast.pyx:13-152", "ctc_fast.pyx:154-187", "brnnet.py:10-277", "sgd.py:91-161"):
+    for cite in ("ctc_fast.pyx:13-152", "ctc_fast.pyx:154-187", "brnnet.py:10-277", "sgd.py:91-161",
+                 "ctc_fast_blankforce.pyx:13-113", "rnnet.py:91-191", "nnet.py:57-113"):
         assert cite in src
 
 
@@ -51,6 +52,13 @@ def test_param_layout_matches_reference_stack():
     # temporalLayer >= numLayers+1 or <= 0 -> no temporal tensors
     cfg2 = _ctcb.BrnnConfig(41, 62, 512, 2, 0, 200, 32, 30, 0.0, 20.0)
     assert _ctcb.lib.ctcb_brnn_num_tensors(ctypes.byref(cfg2)) == 6
+    # uni-directional: one recurrent matrix + its dummy bias (rnnet.py:57-65)
+    cfg3 = _ctcb.BrnnConfig(41, 62, 512, 2, 1, 200, 32, 30, 0.0, 20.0, 1)
+    assert _ctcb.lib.ctcb_brnn_num_tensors(ctypes.byref(cfg3)) == 8
+    assert _ctcb.lib.ctcb_brnn_tensor_info(ctypes.byref(cfg3), 6, ctypes.byref(off), ctypes.byref(r), ctypes.byref(c)) == 0
+    assert (r.value, c.value) == (512, 512)
+    assert _ctcb.lib.ctcb_ctc_blankforce_workspace_bytes(4, 100, 61) == 4 * 100 * 61 * 8
+    assert _ctcb.lib.ctcb_ctc_blankforce_workspace_bytes(4, 100, 1025) == 0
 
 
 def test_error_reporting():

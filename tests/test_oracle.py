@@ -115,3 +115,75 @@ def test_brnn_float32_mode_close_to_float64():
         outs.append((costs, np.concatenate([g[0].ravel() for g in grad]).astype(np.float64)))
     assert np.allclose(outs[0][0], outs[1][0], rtol=1e-4)
     assert np.linalg.norm(outs[0][1] - outs[1][1]) / np.linalg.norm(outs[0][1]) < 1e-4
+
+
+# ---- blank-forced CTC (ctc_fast_blankforce.pyx) and the uni-directional / feed-forward nets ------------
+@pytest.mark.parametrize("name", recipes.ALL_BF)
+def test_blankforce_restatement_matches_golden(name, golden_bf):
+    probs, seq = recipes.bf_case(name)
+    nll, grad, skip = ctc_oracle.ctc_loss_blankforce(np.asfortranarray(probs.astype(np.float64)), seq)
+    assert bool(golden_bf[name + "/skip"]) == skip and not skip
+    g_nll = float(golden_bf[name + "/nll"])
+    assert abs(nll - g_nll) <= REL * abs(g_nll)
+    st = recipes.golden_stride(*probs.shape)
+    np.testing.assert_allclose(grad[:, ::st], golden_bf[name + "/grad"], rtol=0, atol=2e-7)
+    assert abs(np.linalg.norm(grad) - float(golden_bf[name + "/gradnorm"])) <= 1e-10
+
+
+@pytest.mark.skipif(ctc_oracle.ref_module("ctc_fast_blankforce") is None, reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", recipes.ALL_BF)
+def test_blankforce_restatement_matches_reference_live(name):
+    probs, seq = recipes.bf_case(name)
+    p64 = np.asfortranarray(probs.astype(np.float64))
+    nll, grad, skip = ctc_oracle.ctc_loss_blankforce(p64, seq)
+    r_nll, r_grad, r_skip = ctc_oracle.ref_ctc_loss_blankforce(p64, seq)
+    assert skip == r_skip and nll == r_nll and np.array_equal(grad, r_grad)     # bit-exact
+    hyp = ctc_oracle.decode_best_path_blankforce(p64)
+    assert hyp == list(ctc_oracle.ref_module("ctc_fast_blankforce").decode_best_path(p64))
+
+
+def test_blankforce_zero_probability_skips():
+    """A zero frame normaliser is the reference's ZeroDivisionError -> skip (ctc_fast_blankforce.pyx:108-110)."""
+    probs, seq = recipes.bf_case("bf_small")
+    p64 = np.asfortranarray(probs.astype(np.float64))
+    p64[:, 4] = 0.0
+    _, _, skip = ctc_oracle.ctc_loss_blankforce(p64, seq)
+    assert skip
+    if ctc_oracle.ref_module("ctc_fast_blankforce") is not None:
+        assert ctc_oracle.ref_ctc_loss_blankforce(p64, seq)[2]
+
+
+@pytest.mark.parametrize("kw", [dict(temporalLayer=2, unidirectional=True), dict(temporalLayer=-1)])
+def test_rnn_variants_gradcheck(kw):
+    """rnnet.py / nnet.py restatements: analytic vs central differences, the reference's own 1e-4 bound."""
+    rng = np.random.RandomState(4)
+    np.random.seed(4)
+    nn = brnn_oracle.NNet(7, 5, 12, 3, 9, dtype=np.float64, round_f32=False, **kw)
+    nn.initParams()
+    assert len(nn.stack) == 4 + (1 if kw.get("unidirectional") else 0)          # rnnet.py:38-65 / nnet.py:22-23
+    data = rng.randn(7, 9)
+    labels = np.array([1, 2, 2, 4], dtype=np.int32)
+    cost, grad, _ = nn.costAndGrad(data, labels)
+    grad = [[dw.copy(), db.copy()] for dw, db in grad]
+    eps = 1e-6
+    for pi, (w, b) in enumerate(nn.stack):
+        for _ in range(6):
+            i, j = rng.randint(w.shape[0]), rng.randint(w.shape[1])
+            w[i, j] += eps; cp = nn.costAndGrad(data, labels)[0]
+            w[i, j] -= 2 * eps; cm = nn.costAndGrad(data, labels)[0]
+            w[i, j] += eps
+            assert abs(grad[pi][0][i, j] - (cp - cm) / (2 * eps)) < 1e-4
+
+
+def test_rnn_variants_match_golden(golden_rnn):
+    datas, labelss = recipes.rnn_variant_batch()
+    for tag, _ in recipes.RNN_VARIANTS:
+        nn = recipes.rnn_variant_net(brnn_oracle.NNet, tag, dtype=np.float64)
+        recipes.rnn_variant_perturb(nn.stack, tag)
+        for i, (w, b) in enumerate(nn.stack):
+            assert np.array_equal(w.astype(np.float32), golden_rnn["%s/w%d" % (tag, i)])
+        costs, grad, skips = nn.costAndGradBatch(datas, labelss)
+        np.testing.assert_allclose(costs, golden_rnn[tag + "/costs"], rtol=1e-9)
+        for i, (dw, db) in enumerate(grad):
+            np.testing.assert_allclose(dw, golden_rnn["%s/dw%d" % (tag, i)], rtol=1e-9, atol=1e-12)
+    assert int(golden_rnn["uni/clip_hits"]) > 0
