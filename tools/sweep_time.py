@@ -24,6 +24,6 @@ for name, fn in (("fwd", fwd), ("bptt", bwd)):
     e0.record()
     for _ in range(20): fn()
     e1.record(); torch.cuda.synchronize()
-    print("%s opt=%s sweep=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
-        name, os.environ.get("CTCB_SWEEP_OPT", "0"), os.environ.get("CTCB_SWEEP", "auto"), T, B, H,
+    print("%s sweep=%s nb=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
+        name, os.environ.get("CTCB_SWEEP", "auto"), os.environ.get("CTCB_SWEEP_NB", "auto"), T, B, H,
         e0.elapsed_time(e1) / 20, 1e3 * e0.elapsed_time(e1) / 20 / T, int(scr[0])))
