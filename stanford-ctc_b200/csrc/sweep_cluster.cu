@@ -54,11 +54,11 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-// 1-D bulk async copy: this CTA's shared memory -> a cluster peer's shared memory, signalling the
-// peer's mbarrier with the byte count when the data has landed.
-__device__ __forceinline__ void bulk_push(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
-    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(dst_cluster), "r"(src_cta), "r"(bytes), "r"(bar_cluster) : "memory");
+// Remote 4-byte store into a cluster peer's shared memory that completes 4 bytes of the peer's mbarrier
+// transaction count when it has landed (the consumer's try_wait then orders its reads after the data).
+__device__ __forceinline__ void st_async_f32(uint32_t dst_cluster, float v, uint32_t bar_cluster) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                 ::"r"(dst_cluster), "r"(__float_as_uint(v)), "r"(bar_cluster) : "memory");
 }
 
 // packed two-lane fp32 arithmetic (FFMA2)
@@ -102,9 +102,8 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel(SweepClusterArgs 
     static_assert(KW % 4 == 0 && 64 % KW == 0, "warp slice must not straddle two CTA blocks");
     extern __shared__ __align__(128) float sc_smem[];
     float (*hbuf)[CS * BLKF] = reinterpret_cast<float (*)[CS * BLKF]>(sc_smem);                  // [2][source CTA][utterance][unit]
-    float (*red)[BLKF] = reinterpret_cast<float (*)[BLKF]>(sc_smem + 2 * CS * BLKF);             // [16 warps][utterance][unit]
-    float (*stage)[BLKF] = reinterpret_cast<float (*)[BLKF]>(sc_smem + (2 * CS + 16) * BLKF);    // [2][utterance][unit]
-    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sc_smem + (2 * CS + 18) * BLKF);
+    float (*red)[16][BLKF] = reinterpret_cast<float (*)[16][BLKF]>(sc_smem + 2 * CS * BLKF);     // [2][16 warps][utterance][unit]
+    unsigned long long *mbar = reinterpret_cast<unsigned long long *>(sc_smem + (2 * CS + 32) * BLKF);
 
     const int B = a.B, T = a.T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -119,15 +118,15 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel(SweepClusterArgs 
     const int j0 = rank * 64;
     const int k0 = warp * KW;
 
-    unsigned long long w2[2][KW / 2];
+    // w2[k] = weights of output units (2*lane, 2*lane + 1) for input unit k0 + k: the FFMA2 form
+    // (pair of units) x (scalar state value), whose b operand is a plain 32-bit register
+    unsigned long long w2[KW];
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-#pragma unroll
-        for (int p = 0; p < KW / 2; ++p) {
-            const int j = j0 + 2 * lane + r, k = k0 + 2 * p;
-            w2[r][p] = bptt ? pack2(W[(int64_t)k * H + j], W[(int64_t)(k + 1) * H + j])
-                            : pack2(W[(int64_t)j * H + k], W[(int64_t)j * H + k + 1]);
-        }
+    for (int k = 0; k < KW; ++k) {
+        const int j = j0 + 2 * lane, kk = k0 + k;
+        w2[k] = bptt ? pack2(W[(int64_t)kk * H + j], W[(int64_t)kk * H + j + 1])
+                     : pack2(W[(int64_t)j * H + kk], W[(int64_t)(j + 1) * H + kk]);
+    }
 
     const uint32_t bar0 = smem_u32(&mbar[0]), bar1 = smem_u32(&mbar[1]);
     if (tid == 0) {
@@ -172,29 +171,29 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel(SweepClusterArgs 
                 }
             }
             const float *hs = &hbuf[s & 1][hoff];
-            unsigned long long acc2[2][NB];
+            unsigned long long acc2[NB];
 #pragma unroll
             for (int u = 0; u < NB; ++u) {
 #pragma unroll
                 for (int q = 0; q < KW / 4; ++q) {
-                    const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(hs + u * 64 + 4 * q);   // broadcast
-                    if (q == 0) {
-                        acc2[0][u] = 0ull; acc2[1][u] = 0ull;
-                    }
-                    ffma2(acc2[0][u], w2[0][2 * q], hv.x);
-                    ffma2(acc2[1][u], w2[1][2 * q], hv.x);
-                    ffma2(acc2[0][u], w2[0][2 * q + 1], hv.y);
-                    ffma2(acc2[1][u], w2[1][2 * q + 1], hv.y);
+                    const float4 hv = *reinterpret_cast<const float4 *>(hs + u * 64 + 4 * q);   // broadcast
+                    if (q == 0) acc2[u] = 0ull;
+                    ffma2(acc2[u], w2[4 * q], pack2(hv.x, hv.x));
+                    ffma2(acc2[u], w2[4 * q + 1], pack2(hv.y, hv.y));
+                    ffma2(acc2[u], w2[4 * q + 2], pack2(hv.z, hv.z));
+                    ffma2(acc2[u], w2[4 * q + 3], pack2(hv.w, hv.w));
                 }
             }
 #pragma unroll
             for (int u = 0; u < NB; ++u)
-                *reinterpret_cast<float2 *>(&red[warp][u * 64 + 2 * lane]) = make_float2(sum2(acc2[0][u]), sum2(acc2[1][u]));
-            __syncthreads();
+                *reinterpret_cast<unsigned long long *>(&red[s & 1][warp][u * 64 + 2 * lane]) = acc2[u];
+            __syncthreads();            // the only CTA barrier of the step (red is double-buffered)
+            // every warp is past its wait on this step's barrier: arm it for step s + 2
+            if (tid == 0 && s + 2 < T) mbar_arrive_expect_tx(bar, CS * BLK_BYTES);
             if (owner) {
                 float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                for (int w = 0; w < 16; w += 2) { s0 += red[w][tid]; s1 += red[w + 1][tid]; }
+                for (int w = 0; w < 16; w += 2) { s0 += red[s & 1][w][tid]; s1 += red[s & 1][w + 1][tid]; }
                 sum = s0 + s1;
             }
         }
@@ -206,27 +205,21 @@ __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel(SweepClusterArgs 
             if (t >= Tb) v = 0.f;
             out[((int64_t)t * B + b) * H + oj] = v;
         }
-        if (s + 1 < T) {
-            if (owner) stage[s & 1][tid] = v;
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            __syncthreads();
-            if (warp == 0) {
-                if (s > 0 && lane == 0) mbar_arrive_expect_tx((s & 1) ? bar1 : bar0, CS * BLK_BYTES);
-                __syncwarp();
-                if (lane < CS) {
-                    const int nb = (s + 1) & 1;
-                    const uint32_t dst = map_to_cta(smem_u32(&hbuf[nb][rank * BLKF]), (uint32_t)lane);
-                    const uint32_t rbar = map_to_cta(nb ? bar1 : bar0, (uint32_t)lane);
-                    bulk_push(dst, smem_u32(&stage[s & 1][0]), BLK_BYTES, rbar);
-                }
-            }
+        if (owner && s + 1 < T) {
+            // hand the new state to every CTA of the cluster (this one included): one remote 4-byte store per
+            // peer, each completing 4 bytes on the peer's barrier of step s + 1
+            const int nb = (s + 1) & 1;
+            const uint32_t dst = smem_u32(&hbuf[nb][rank * BLKF + tid]);
+            const uint32_t dbar = nb ? bar1 : bar0;
+#pragma unroll
+            for (int c = 0; c < CS; ++c) st_async_f32(map_to_cta(dst, (uint32_t)c), v, map_to_cta(dbar, (uint32_t)c));
         }
     }
     cluster_sync_all();
 }
 
 static constexpr size_t cluster_smem_bytes(int KI, int NB) {
-    return sizeof(float) * (size_t)(2 * (KI / 2) + 18) * (size_t)(NB * 64) + 16;
+    return sizeof(float) * (size_t)(2 * (KI / 2) + 32) * (size_t)(NB * 64) + 16;
 }
 
 template <int KI, int NB>
