@@ -367,13 +367,20 @@ def run_ours(args, c):
         fl = 2.0 * 2.0 * (T - 1) * H * H * Bl
         launch_ms = sweep_ms / 2.0 if sweep_ms else float("nan")
         ach = fl / (launch_ms * 1e-3) / 1e12
-        roof = {"kernel": "sweep_cluster_kernel_v3 / sweep_kernel (recurrent forward + BPTT sweeps, 2 launches/step)", "bound": "tensor",
+        # yardstick that fits the arithmetic: the packed-fp32 (FFMA2) pipe, measured at 92 FMA/clk/SM on this part
+        # (tools/micro/mma_rate.cu: 2.8 cycles per FFMA2 warp instruction per SM sub-partition) x 148 SMs x SM clock
+        fp32_peak = 92.0 * 148 * 2.0 * (clocks.get("sm_mhz") or 1965.0) * 1e6 / 1e12
+        roof = {"kernel": "sweep_cluster_kernel (H<=512) / sweep_kernel: recurrent forward + BPTT sweeps, 2 launches/step",
+                "bound": "tensor",
                 "achieved": ach, "peak": pk["tf_sust"], "unit": "TFLOP/s", "frac": ach / pk["tf_sust"],
-                "traffic": ncu_traffic("sweep_cluster_kernel_v3") if (c["H"] == 512 and Bl == 32) else None,
+                "traffic": ncu_traffic("sweep_cluster_kernel") if (c["H"] == 512 and Bl == 32) else None,
                 "peak_source": pk["src"] + " bf16 sustained",
                 "share_of_step": sweep_ms / tot if tot else None, "dominant_phase": dom,
-                "note": "exact-fp32 FFMA2 recurrence, serial in t (T-1 dependent steps of a 32x512x512 product): bound by issue "
-                        "rate and the per-step DSMEM exchange, not by the tensor pipe; the schema's tensor peak is only a yardstick"}
+                "fp32_pipe_peak_tflops": fp32_peak, "frac_of_fp32_pipe": ach / fp32_peak,
+                "note": "exact-fp32 FFMA2 recurrence, serial in t (T-1 dependent steps of a BxHxH product per direction): "
+                        "bound by the fp32 FMA pipe on the 112 SMs that 14 clusters of 8 CTAs occupy plus the per-step "
+                        "cluster exchange, not by the tensor pipe; the schema's tensor peak is only a yardstick, "
+                        "frac_of_fp32_pipe is the meaningful fraction"}
 
     # ---------------------------------------------------------------- CTC kernel in isolation (HBM roofline)
     roof_ctc = None

@@ -22,6 +22,7 @@
 // recurrences run on e = exp(x - max) and the log-partition is added to the loss separately.
 #include "common.cuh"
 #include <math_constants.h>
+#include <stdlib.h>
 
 namespace ctcb {
 
@@ -102,54 +103,367 @@ __device__ __forceinline__ double pow2_from_field(int biased) { return __hiloint
 
 constexpr float GFIX = 1073741824.f;   // occupancies are accumulated as 2^30 fixed point (native ATOMS.ADD)
 
-// One warp per utterance.  alpha/beta live in registers in FLOAT64 (the reference's own arithmetic,
-// ctc_fast.pyx:23-37): float32 cannot hold the product of the alpha and beta tails, which is what the
-// gradient is made of.  Instead of dividing by the frame normaliser every frame (a warp reduction on
-// the serial chain) the state is rescaled by a power of two derived from the PREVIOUS frame's largest
-// exponent (one REDUX.MAX off the chain); the accumulated exponent goes into the loss.
+// alpha/beta live in registers in FLOAT64 (the reference's own arithmetic, ctc_fast.pyx:23-37): float32
+// cannot hold the product of the alpha and beta tails, which is what the gradient is made of.  Instead of
+// dividing by the frame normaliser every frame (a warp reduction on the serial chain) the state is rescaled
+// by a power of two derived from the PREVIOUS frame's largest exponent (one REDUX.MAX off the chain); the
+// accumulated exponent goes into the loss.
+//
+// Per-lane view of one utterance: pairs i = lane*P + j  (blank s = 2i, label s = 2i+1).
+template <int P>
+struct LaneLabels {
+    int lab[P];
+    bool allow_a[P], allow_b[P];
+    int nlab, L;
+    __device__ __forceinline__ void load(const CtcArgs &a, int lo, int nl, int lane) {
+        nlab = nl; L = 2 * nl + 1;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const int i = lane * P + j;
+            lab[j] = (i < nlab) ? a.labels[lo + i] : -1;
+            const int lprev = (i >= 1 && i < nlab) ? a.labels[lo + i - 1] : -1;
+            const int lnext = (i + 1 < nlab) ? a.labels[lo + i + 1] : -1;
+            allow_a[j] = (i >= 1 && i < nlab && lab[j] != lprev);       // ctc_fast.pyx:64-68
+            allow_b[j] = (i + 1 < nlab && lab[j] != lnext);             // ctc_fast.pyx:104-108
+        }
+    }
+};
+
+// One frame of the alpha recurrence (:49-76) on e-values `row`.  ab/al: blank/label states of the previous
+// frame in, of frame t out (scaled by 2^kscale of the previous frame).  Returns false when all mass is gone.
+template <int P>
+__device__ __forceinline__ bool alpha_frame(const LaneLabels<P> &q, const float *row, int blank, int lane, int T, int t,
+                                            double (&ab)[P], double (&al)[P], int &kscale, int &S) {
+    const double eb = (double)row[blank];
+    int start = 2 * (T - t);
+    start = (q.L <= start || t == 0) ? 0 : q.L - start;   // the reference sets frame 0 without a window (:42-47)
+    double pl = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
+    if (lane == 0) pl = 0.0;
+    const double sc = pow2_from_field(1023 + kscale);
+    double mx = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = lane * P + j;
+        const double el = (q.lab[j] >= 0) ? (double)row[q.lab[j]] : 0.0;
+        double b = (ab[j] + pl) * eb;
+        double l = (al[j] + ab[j] + (q.allow_a[j] ? pl : 0.0)) * el;
+        if (i > q.nlab) b = 0.0;
+        if (start > 0) {                    // warp-uniform: only the last |l| frames prune
+            if (2 * i < start) b = 0.0;
+            if (2 * i + 1 < start) l = 0.0;
+        }
+        pl = al[j];
+        ab[j] = b * sc;
+        al[j] = l * sc;
+        mx = fmax(mx, fmax(ab[j], al[j]));
+    }
+    S += kscale;
+    const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
+    if (emax == 0) return false;            // all mass gone: ZeroDivisionError in :70-76
+    kscale = 1023 - emax;
+    return true;
+}
+
+// One frame of the beta recurrence (:85-114).  bb/bl: states of frame t+1 in, of frame t out.  pb/pll receive the
+// (scaled) PRE-emission sums of frame t: beta[s,t] = pre[s] * p[lab(s),t], so alpha*beta/p = alpha*pre.
+template <int P>
+__device__ __forceinline__ bool beta_frame(const LaneLabels<P> &q, const float *row, int blank, int lane, int t,
+                                           double (&bb)[P], double (&bl)[P], int &kscale, double (&pb)[P],
+                                           double (&pll)[P]) {
+    const double eb = (double)row[blank];
+    const int end = min(2 * t + 2, q.L);
+    double nxb = __shfl_down_sync(0xffffffffu, bb[0], 1);
+    double nxl = __shfl_down_sync(0xffffffffu, bl[0], 1);
+    if (lane == 31) nxb = nxl = 0.0;
+    const double sc = pow2_from_field(1023 + kscale);
+    double nb[P], mx = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = lane * P + j;
+        const double el = (q.lab[j] >= 0) ? (double)row[q.lab[j]] : 0.0;
+        const double b1 = (j + 1 < P) ? bb[(j + 1 < P) ? j + 1 : j] : nxb;
+        const double l1 = (j + 1 < P) ? bl[(j + 1 < P) ? j + 1 : j] : nxl;
+        double xb = bb[j] + bl[j];
+        double xl = bl[j] + b1 + (q.allow_b[j] ? l1 : 0.0);
+        if (i > q.nlab) xb = 0.0;
+        if (q.lab[j] < 0) xl = 0.0;
+        if (end < q.L) {                    // warp-uniform: only the first |l| frames prune
+            if (2 * i >= end) xb = 0.0;
+            if (2 * i + 1 >= end) xl = 0.0;
+        }
+        xb *= sc;
+        xl *= sc;
+        pb[j] = xb;
+        pll[j] = xl;
+        nb[j] = xb * eb;
+        const double lnew = xl * el;
+        mx = fmax(mx, fmax(nb[j], lnew));
+        bl[j] = lnew;                       // old bl[j] no longer needed by later j
+    }
+#pragma unroll
+    for (int j = 0; j < P; ++j) bb[j] = nb[j];
+    const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
+    kscale = 1023 - emax;
+    return emax != 0;                       // beta mass gone: ZeroDivisionError in :109-114
+}
+
+// Occupancies of one frame from alpha-tilde (xb, xl) and the beta pre-emission sums (pb, pll), any power-of-two
+// scaling of either: numerators alpha*pre (no division by p, :117-136), normalised by their sum (absum, :133-145)
+// and scattered into the frame's row of the shared occupancy tile as 2^30 fixed point.
+// absum and the blank occupancy come without a float64 butterfly: scale the lane sums by a common power of two
+// (largest lane exponent, one REDUX.MAX), quantise to 2^-24 of it and add with the integer REDUX.ADD.  alpha*beta
+// can underflow float64 for every state of a frame (thousands of uninformative frames); the reference then leaves
+// the frame at grad = p (absum == 0 -> :141-145, no skip), which is what wsum == 0 does here.
+template <int P>
+__device__ __forceinline__ void occupancy_frame(const LaneLabels<P> &q, int blank, int lane, const double (&xb)[P],
+                                                const double (&xl)[P], const double (&pb)[P], const double (&pll)[P],
+                                                unsigned *grow) {
+    double nl[P], w = 0.0, wb = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const double wbj = xb[j] * pb[j];
+        nl[j] = xl[j] * pll[j];
+        wb += wbj;
+        w += wbj + nl[j];
+    }
+    const int ew = __reduce_max_sync(0xffffffffu, dexp_field(w));
+    const double wscale = (ew >= 24) ? pow2_from_field(2070 - ew) : 0.0;   // largest lane sum -> [2^24, 2^25)
+    const unsigned wq = (unsigned)__double2uint_rz(w * wscale);
+    const unsigned wbq = (unsigned)__double2uint_rz(wb * wscale);
+    const unsigned wsum = __reduce_add_sync(0xffffffffu, wq);
+    const unsigned wbsum = __reduce_add_sync(0xffffffffu, wbq);
+    const float winv = (wsum > 0u) ? 1.f / (float)wsum : 0.f;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const float g = (float)(nl[j] * wscale) * winv;
+        if (g > 0.f) atomicAdd(grow + q.lab[j], (unsigned)(g * GFIX + 0.5f));
+    }
+    if (lane == 0) atomicAdd(grow + blank, (unsigned)((float)wbsum * winv * GFIX + 0.5f));
+}
+
+// Everything one warp needs to walk over the time tiles of one utterance.
+struct WarpCtx {
+    const float *base;      // activations of the utterance
+    float *gbase;           // its gradient
+    double *wsu;            // its trellis spill, [T][64P] doubles
+    float *te0, *tg;        // shared: nbuf e tiles, one occupancy tile
+    int T, ntiles, nbuf, lane;
+};
+
+// Load tile `tile` (double-buffered: the copy of `next` -- or -1 -- is issued first and stays in flight).
+__device__ __forceinline__ float *fetch_tile(const CtcArgs &a, const WarpCtx &c, int tile, int next) {
+    float *te = c.te0 + ((c.nbuf == 2) ? (tile & 1) : 0) * TT * a.Kp;
+    if (c.nbuf == 2 && next >= 0) {
+        issue_tile(a, c.base, next * TT, c.T, c.te0 + (next & 1) * TT * a.Kp, c.lane);
+        cp_async_wait<1>();
+    } else {
+        if (c.nbuf == 1) issue_tile(a, c.base, tile * TT, c.T, te, c.lane);
+        cp_async_wait<0>();
+    }
+    __syncwarp();
+    return te;
+}
+
+// grad = p - occupancy (:139-145) for the rmax frames of a tile, coalesced row stores
+__device__ __forceinline__ void tile_epilogue(const CtcArgs &a, const WarpCtx &c, int t0, int rmax, const float *te,
+                                              const unsigned *tgu, float my_Zinv) {
+    for (int r = 0; r < rmax; ++r) {
+        const float zinv = __shfl_sync(0xffffffffu, my_Zinv, r);
+        float *orow = c.gbase + (int64_t)(t0 + r) * a.fs;
+        for (int k = c.lane; k < a.K; k += 32)
+            orow[k] = te[r * a.Kp + k] * zinv - (float)tgu[r * a.Kp + k] * (1.f / GFIX);
+    }
+    __syncwarp();
+}
+
+// alpha over tiles [tile_from, tile_to), ascending (:42-76).  COMBINE = false: the scaled states of every frame are
+// spilled to the workspace for a later beta sweep.  COMBINE = true: the workspace already holds the beta
+// pre-emission sums of these frames (stored by beta_tiles<P,false>); occupancies and gradient are produced here.
+template <int P, bool COMBINE>
+__device__ __forceinline__ bool alpha_tiles(const CtcArgs &a, const WarpCtx &c, const LaneLabels<P> &q, int tile_from,
+                                            int tile_to, bool recur, double (&ab)[P], double (&al)[P], int &kscale,
+                                            int &S, float &logZ) {
+    constexpr int LP = 64 * P;
+    const int lane = c.lane, T = c.T;
+    if (c.nbuf == 2 && tile_from < tile_to) issue_tile(a, c.base, tile_from * TT, T, c.te0 + (tile_from & 1) * TT * a.Kp, lane);
+    for (int tile = tile_from; tile < tile_to; ++tile) {
+        const int t0 = tile * TT;
+        const float *te = fetch_tile(a, c, tile, (tile + 1 < tile_to) ? tile + 1 : -1);
+        const float Z = tile_stats(a, t0, T, const_cast<float *>(te), lane);
+        if (lane < TT) logZ += logf(Z);
+        const int rmax = min(TT, T - t0);
+        unsigned *tgu = reinterpret_cast<unsigned *>(c.tg);
+        if (COMBINE) {
+            for (int idx = lane; idx < TT * a.Kp; idx += 32) tgu[idx] = 0u;
+            __syncwarp();
+        }
+        if (recur) {
+            double2 pn[P];      // beta pre-emission sums of the next frame to be processed (prefetched)
+            if (COMBINE) {
+                const double2 *prow = reinterpret_cast<const double2 *>(c.wsu + (int64_t)t0 * LP) + lane * P;
+#pragma unroll
+                for (int j = 0; j < P; ++j) pn[j] = prow[j];
+            }
+            for (int r = 0; r < rmax; ++r) {
+                const int t = t0 + r;
+                double2 pv[P];
+                if (COMBINE) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) pv[j] = pn[j];
+                    const double *pf = c.wsu + (int64_t)min(t + 4, T - 1) * LP + lane * 2 * P;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                    if (P > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 16));
+                    const double2 *prow = reinterpret_cast<const double2 *>(c.wsu + (int64_t)min(t + 1, T - 1) * LP) + lane * P;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) pn[j] = prow[j];
+                }
+                if (!alpha_frame<P>(q, te + r * a.Kp, a.blank, lane, T, t, ab, al, kscale, S)) return false;
+                if (COMBINE) {
+                    double pb[P], pll[P];
+#pragma unroll
+                    for (int j = 0; j < P; ++j) { pb[j] = pv[j].x; pll[j] = pv[j].y; }
+                    occupancy_frame<P>(q, a.blank, lane, ab, al, pb, pll, tgu + r * a.Kp);
+                } else {
+                    double2 *wrow = reinterpret_cast<double2 *>(c.wsu + (int64_t)t * LP) + lane * P;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) wrow[j] = make_double2(ab[j], al[j]);
+                }
+            }
+        }
+        __syncwarp();
+        if (COMBINE) tile_epilogue(a, c, t0, rmax, te, tgu, 1.f / Z);
+    }
+    return true;
+}
+
+// beta over tiles tile_from, tile_from-1, ..., tile_to (descending, :78-114).  COMBINE = true: the workspace holds
+// alpha-tilde of these frames; occupancies and gradient are produced here.  COMBINE = false: the pre-emission sums
+// of every frame are spilled for a later alpha_tiles<P,true>.
+template <int P, bool COMBINE>
+__device__ __forceinline__ bool beta_tiles(const CtcArgs &a, const WarpCtx &c, const LaneLabels<P> &q, int tile_from,
+                                           int tile_to, bool recur, double (&bb)[P], double (&bl)[P], int &kscale) {
+    constexpr int LP = 64 * P;
+    const int lane = c.lane, T = c.T;
+    if (c.nbuf == 2 && tile_from >= tile_to) issue_tile(a, c.base, tile_from * TT, T, c.te0 + (tile_from & 1) * TT * a.Kp, lane);
+    for (int tile = tile_from; tile >= tile_to; --tile) {
+        const int t0 = tile * TT;
+        const float *te = fetch_tile(a, c, tile, (tile > tile_to) ? tile - 1 : -1);
+        const float Z = tile_stats(a, t0, T, const_cast<float *>(te), lane);
+        unsigned *tgu = reinterpret_cast<unsigned *>(c.tg);
+        if (COMBINE) {
+            for (int idx = lane; idx < TT * a.Kp; idx += 32) tgu[idx] = 0u;
+            __syncwarp();
+        }
+        const int rmax = min(TT, T - t0);
+        if (recur) {
+            double2 an[P];   // alpha-tilde of the next frame to be processed (prefetched)
+            if (COMBINE) {
+                const double2 *arow = reinterpret_cast<const double2 *>(c.wsu + (int64_t)(t0 + rmax - 1) * LP) + lane * P;
+#pragma unroll
+                for (int j = 0; j < P; ++j) an[j] = arow[j];
+            }
+            for (int r = rmax - 1; r >= 0; --r) {
+                const int t = t0 + r;
+                double2 av[P];
+                if (COMBINE) {
+#pragma unroll
+                    for (int j = 0; j < P; ++j) av[j] = an[j];
+                    // pull the alpha-tilde row needed 4 frames from now into L1 (the spill sits in L2/HBM), then
+                    // load the row of the next frame (t-1, clamped: the value is unused at t = 0)
+                    const double *pf = c.wsu + (int64_t)max(t - 4, 0) * LP + lane * 2 * P;
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
+                    if (P > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 16));
+                    const double2 *arow = reinterpret_cast<const double2 *>(c.wsu + (int64_t)max(t - 1, 0) * LP) + lane * P;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) an[j] = arow[j];
+                }
+                double pb[P], pll[P];
+                if (!beta_frame<P>(q, te + r * a.Kp, a.blank, lane, t, bb, bl, kscale, pb, pll)) return false;
+                if (COMBINE) {
+                    double xb[P], xl[P];
+#pragma unroll
+                    for (int j = 0; j < P; ++j) { xb[j] = av[j].x; xl[j] = av[j].y; }
+                    occupancy_frame<P>(q, a.blank, lane, xb, xl, pb, pll, tgu + r * a.Kp);
+                } else {
+                    double2 *wrow = reinterpret_cast<double2 *>(c.wsu + (int64_t)t * LP) + lane * P;
+#pragma unroll
+                    for (int j = 0; j < P; ++j) wrow[j] = make_double2(pb[j], pll[j]);
+                }
+            }
+        }
+        __syncwarp();
+        if (COMBINE) tile_epilogue(a, c, t0, rmax, te, tgu, 1.f / Z);
+    }
+    return true;
+}
+
+// p(l|x) at the last frame = alpha[L-1] + alpha[L-2] (:76), in the scaled domain
+// A one-frame utterance never leaves the reference's un-windowed initialisation, whose normaliser is
+// alpha[0,0] + alpha[1,0] (:42-47): that sum is what it returns then.
+template <int P>
+__device__ __forceinline__ double final_mass(const LaneLabels<P> &q, int lane, int T, const double (&ab)[P],
+                                             const double (&al)[P]) {
+    double fs = 0.0;
+#pragma unroll
+    for (int j = 0; j < P; ++j) {
+        const int i = lane * P + j;
+        if (T == 1) {
+            if (i == 0) fs += ab[j] + al[j];
+        } else {
+            if (i == q.nlab) fs += ab[j];
+            if (i == q.nlab - 1) fs += al[j];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
+    return fs;
+}
+
+__device__ __forceinline__ void zero_rows(const CtcArgs &a, float *gbase, int t_from, int t_to, int lane, int nlanes) {
+    for (int t = t_from; t < t_to; ++t) {
+        float *orow = gbase + (int64_t)t * a.fs;
+        for (int k = lane; k < a.K; k += nlanes) orow[k] = 0.f;
+    }
+}
+
+__device__ __forceinline__ void write_loss(const CtcArgs &a, int u, bool short_utt, bool fail, double final_sum, int S,
+                                           float lz) {
+    float nll;
+    if (short_utt && !fail) nll = CUDART_INF_F;    // every window empty: the reference returns (inf, p, False)
+    else nll = (float)(-(log(final_sum) - (double)S * 0.69314718055994530942 - (double)lz));
+    a.nll[u] = nll;
+    a.skip[u] = fail ? 1 : 0;
+}
+
+// Throughput shape: ONE WARP per utterance -- alpha over all frames (spilled), then beta with the gradient.
 template <int P>
 __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
     extern __shared__ float smem[];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int u = blockIdx.x * (blockDim.x >> 5) + wib;
     if (u >= a.B) return;
-    const int K = a.K, Kp = a.Kp, blank = a.blank;
     // nbuf = 2: two e tiles (the copy of tile n+1 overlaps the work on tile n; used for small batches, where one
     // warp has an SM almost to itself); nbuf = 1: one e tile, 1/3 less shared memory -> 24 instead of 16 warps per
     // SM, the other warps hide the copy (large batches).  Then the occupancy tile.
-    const int nbuf = a.nbuf;
-    float *te0 = smem + (size_t)wib * (nbuf + 1) * TT * Kp;
-    float *tg = te0 + nbuf * TT * Kp;
-    const int T = min(a.Tlen[u], a.Tmax);
+    WarpCtx c;
+    c.nbuf = a.nbuf; c.lane = lane;
+    c.te0 = smem + (size_t)wib * (a.nbuf + 1) * TT * a.Kp;
+    c.tg = c.te0 + a.nbuf * TT * a.Kp;
+    c.T = min(a.Tlen[u], a.Tmax);
+    c.ntiles = (c.T + TT - 1) / TT;
+    c.base = a.acts + (int64_t)u * a.us;
+    c.gbase = a.grad + (int64_t)u * a.us;
+    c.wsu = reinterpret_cast<double *>(a.ws) + (int64_t)u * a.ws_utt;
     const int lo = a.loff[u];
-    const int nlab = a.loff[u + 1] - lo;
-    const int L = 2 * nlab + 1;
-    const float *base = a.acts + (int64_t)u * a.us;
-    float *gbase = a.grad + (int64_t)u * a.us;
-    double *wsu = reinterpret_cast<double *>(a.ws) + (int64_t)u * a.ws_utt;
-    constexpr int LP = 64 * P;  // padded trellis row (doubles) in the workspace
+    LaneLabels<P> q;
+    q.load(a, lo, a.loff[u + 1] - lo, lane);
 
-    // per-lane label data for pairs i = lane*P + j  (blank s = 2i, label s = 2i+1)
-    int lab[P];
-    bool allow_a[P], allow_b[P];
-#pragma unroll
-    for (int j = 0; j < P; ++j) {
-        const int i = lane * P + j;
-        lab[j] = (i < nlab) ? a.labels[lo + i] : -1;
-        const int lprev = (i >= 1 && i < nlab) ? a.labels[lo + i - 1] : -1;
-        const int lnext = (i + 1 < nlab) ? a.labels[lo + i + 1] : -1;
-        allow_a[j] = (i >= 1 && i < nlab && lab[j] != lprev);       // ctc_fast.pyx:64-68
-        allow_b[j] = (i + 1 < nlab && lab[j] != lnext);             // ctc_fast.pyx:104-108
-    }
-
-    const bool short_utt = (T < nlab);  // every window empty: reference returns (inf, p, False)
-    bool fail = (T <= 0);
+    const bool short_utt = (c.T < q.nlab);
+    bool fail = (c.T <= 0);
     float logZ = 0.f;     // lanes < TT accumulate log Z of the rows they own
     int S = 0;            // accumulated power-of-two scaling of alpha
     double final_sum = 1.0;
-    const int ntiles = (T + TT - 1) / TT;
 
-    // ------------------------------------------------------------------ alpha sweep (:42-76)
     if (!short_utt && !fail) {
         double ab[P], al[P];
 #pragma unroll
@@ -158,74 +472,12 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         // (alpha[0,0] = p_blank, alpha[1,0] = p_label0, ctc_fast.pyx:42-47) -- no special case in the loop
         if (lane == 0) ab[0] = 1.0;
         int kscale = 0;   // power of two applied to the next frame
-        if (nbuf == 2) issue_tile(a, base, 0, T, te0, lane);
-        for (int tile = 0; tile < ntiles && !fail; ++tile) {
-            const int t0 = tile * TT;
-            float *te = te0 + ((nbuf == 2) ? (tile & 1) : 0) * TT * Kp;
-            if (nbuf == 2 && tile + 1 < ntiles) {
-                issue_tile(a, base, t0 + TT, T, te0 + ((tile + 1) & 1) * TT * Kp, lane);
-                cp_async_wait<1>();
-            } else {
-                if (nbuf == 1) issue_tile(a, base, t0, T, te, lane);
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-            const float Z = tile_stats(a, t0, T, te, lane);
-            if (lane < TT) logZ += logf(Z);
-            const int rmax = min(TT, T - t0);
-            for (int r = 0; r < rmax; ++r) {
-                const int t = t0 + r;
-                const float *row = te + r * Kp;
-                const double eb = (double)row[blank];
-                int start = 2 * (T - t);
-                start = (L <= start) ? 0 : L - start;
-                double pl = __shfl_up_sync(0xffffffffu, al[P - 1], 1);
-                if (lane == 0) pl = 0.0;
-                const double sc = pow2_from_field(1023 + kscale);
-                double mx = 0.0;
-#pragma unroll
-                for (int j = 0; j < P; ++j) {
-                    const int i = lane * P + j;
-                    const double el = (lab[j] >= 0) ? (double)row[lab[j]] : 0.0;
-                    double b = (ab[j] + pl) * eb;
-                    double l = (al[j] + ab[j] + (allow_a[j] ? pl : 0.0)) * el;
-                    if (i > nlab) b = 0.0;
-                    if (start > 0) {                    // warp-uniform: only the last |l| frames prune
-                        if (2 * i < start) b = 0.0;
-                        if (2 * i + 1 < start) l = 0.0;
-                    }
-                    pl = al[j];
-                    ab[j] = b * sc;
-                    al[j] = l * sc;
-                    mx = fmax(mx, fmax(ab[j], al[j]));
-                }
-                S += kscale;
-                const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
-                if (emax == 0) { fail = true; break; }      // all mass gone: ZeroDivisionError in :70-76
-                kscale = 1023 - emax;
-                double2 *wrow = reinterpret_cast<double2 *>(wsu + (int64_t)t * LP) + lane * P;
-#pragma unroll
-                for (int j = 0; j < P; ++j) wrow[j] = make_double2(ab[j], al[j]);
-            }
-            __syncwarp();
-        }
-        if (!fail) {   // p(l|x) = alpha[L-1] + alpha[L-2] at the last frame
-            double fs = 0.0;
-#pragma unroll
-            for (int j = 0; j < P; ++j) {
-                const int i = lane * P + j;
-                if (i == nlab) fs += ab[j];
-                if (i == nlab - 1) fs += al[j];
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) fs += __shfl_xor_sync(0xffffffffu, fs, o);
-            final_sum = fs;
-            if (!(fs > 0.0)) fail = true;
+        fail = !alpha_tiles<P, false>(a, c, q, 0, c.ntiles, true, ab, al, kscale, S, logZ);
+        if (!fail) {
+            final_sum = final_mass<P>(q, lane, c.T, ab, al);
+            if (!(final_sum > 0.0)) fail = true;
         }
     }
-
-    // ------------------------------------------------------------------ beta sweep + gradient
-    float my_Zinv = 1.f;
     if (!fail) {
         double bb[P], bl[P];
 #pragma unroll
@@ -234,140 +486,84 @@ __global__ void __launch_bounds__(256) ctc_warp_kernel(CtcArgs a) {
         // pre[L-1] = pre[L-2] = 1 (ctc_fast.pyx:78-83) from the ordinary recurrence
 #pragma unroll
         for (int j = 0; j < P; ++j)
-            if (lane * P + j == nlab) bb[j] = 1.0;
+            if (lane * P + j == q.nlab) bb[j] = 1.0;
         int kscale = 0;
-        if (nbuf == 2) issue_tile(a, base, (ntiles - 1) * TT, T, te0 + ((ntiles - 1) & 1) * TT * Kp, lane);
-        for (int tile = ntiles - 1; tile >= 0 && !fail; --tile) {
-            const int t0 = tile * TT;
-            float *te = te0 + ((nbuf == 2) ? (tile & 1) : 0) * TT * Kp;
-            if (nbuf == 2 && tile > 0) {
-                issue_tile(a, base, t0 - TT, T, te0 + ((tile - 1) & 1) * TT * Kp, lane);
-                cp_async_wait<1>();
-            } else {
-                if (nbuf == 1) issue_tile(a, base, t0, T, te, lane);
-                cp_async_wait<0>();
-            }
-            __syncwarp();
-            const float Z = tile_stats(a, t0, T, te, lane);
-            my_Zinv = 1.f / Z;
-            unsigned *tgu = reinterpret_cast<unsigned *>(tg);
-            for (int idx = lane; idx < TT * Kp; idx += 32) tgu[idx] = 0u;
-            __syncwarp();
-            const int rmax = min(TT, T - t0);
-            if (!short_utt) {
-                double2 an[P];   // alpha-tilde of the next frame to be processed (prefetched)
-                {
-                    const double2 *arow = reinterpret_cast<const double2 *>(wsu + (int64_t)(t0 + rmax - 1) * LP) + lane * P;
-#pragma unroll
-                    for (int j = 0; j < P; ++j) an[j] = arow[j];
-                }
-                for (int r = rmax - 1; r >= 0; --r) {
-                    const int t = t0 + r;
-                    const float *row = te + r * Kp;
-                    unsigned *grow = tgu + r * Kp;
-                    const double eb = (double)row[blank];
-                    double2 av[P];
-#pragma unroll
-                    for (int j = 0; j < P; ++j) av[j] = an[j];
-                    {   // pull the alpha-tilde row needed 4 frames from now into L1 (the spill sits in L2/HBM), then
-                        // load the row of the next frame (t-1, clamped: the value is unused at t = 0)
-                        const double *pf = wsu + (int64_t)max(t - 4, 0) * LP + lane * 2 * P;
-                        asm volatile("prefetch.global.L1 [%0];" ::"l"(pf));
-                        if (P > 8) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf + 16));
-                        const int tp = max(t - 1, 0);
-                        const double2 *arow = reinterpret_cast<const double2 *>(wsu + (int64_t)tp * LP) + lane * P;
-#pragma unroll
-                        for (int j = 0; j < P; ++j) an[j] = arow[j];
-                    }
-                    const int end = min(2 * t + 2, L);
-                    double nxb = __shfl_down_sync(0xffffffffu, bb[0], 1);
-                    double nxl = __shfl_down_sync(0xffffffffu, bl[0], 1);
-                    if (lane == 31) nxb = nxl = 0.0;
-                    const double sc = pow2_from_field(1023 + kscale);
-                    double nb[P], nl[P], w = 0.0, wb = 0.0, mx = 0.0;
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const int i = lane * P + j;
-                        const double el = (lab[j] >= 0) ? (double)row[lab[j]] : 0.0;
-                        const double b1 = (j + 1 < P) ? bb[(j + 1 < P) ? j + 1 : j] : nxb;
-                        const double l1 = (j + 1 < P) ? bl[(j + 1 < P) ? j + 1 : j] : nxl;
-                        // pre-emission sums: beta[s,t] = pre[s] * p[lab(s),t]
-                        double pb = bb[j] + bl[j];
-                        double pll = bl[j] + b1 + (allow_b[j] ? l1 : 0.0);
-                        if (i > nlab) pb = 0.0;
-                        if (lab[j] < 0) pll = 0.0;
-                        if (end < L) {                  // warp-uniform: only the first |l| frames prune
-                            if (2 * i >= end) pb = 0.0;
-                            if (2 * i + 1 >= end) pll = 0.0;
-                        }
-                        pb *= sc;
-                        pll *= sc;
-                        // occupancy numerators alpha*beta/p = alpha * pre  (no division by p, :117-136)
-                        const double wbj = av[j].x * pb;
-                        nl[j] = av[j].y * pll;          // reuse nl[] for the label numerators
-                        wb += wbj;
-                        w += wbj + nl[j];
-                        nb[j] = pb * eb;
-                        const double lnew = pll * el;
-                        mx = fmax(mx, fmax(nb[j], lnew));
-                        bl[j] = lnew;                   // old bl[j] no longer needed by later j
-                    }
-#pragma unroll
-                    for (int j = 0; j < P; ++j) bb[j] = nb[j];
-                    const int emax = __reduce_max_sync(0xffffffffu, dexp_field(mx));
-                    kscale = 1023 - emax;
-                    if (emax == 0) { fail = true; break; }        // beta mass gone: ZeroDivisionError in :109-114
-                    // absum (sum of all numerators) and the blank occupancy without a float64 butterfly: scale the
-                    // lane sums by a common power of two (largest lane exponent, one REDUX.MAX), quantise to 2^-24 of
-                    // it and add with the integer REDUX.ADD.  alpha*beta can underflow float64 for every state of a
-                    // frame (thousands of uninformative frames); the reference then leaves the frame at grad = p
-                    // (absum == 0 -> :141-145, no skip), which is what wsum == 0 does here.
-                    const int ew = __reduce_max_sync(0xffffffffu, dexp_field(w));
-                    const double wscale = (ew >= 24) ? pow2_from_field(2070 - ew) : 0.0;   // largest lane sum -> [2^24, 2^25)
-                    const unsigned wq = (unsigned)__double2uint_rz(w * wscale);
-                    const unsigned wbq = (unsigned)__double2uint_rz(wb * wscale);
-                    const unsigned wsum = __reduce_add_sync(0xffffffffu, wq);
-                    const unsigned wbsum = __reduce_add_sync(0xffffffffu, wbq);
-                    const float winv = (wsum > 0u) ? 1.f / (float)wsum : 0.f;
-#pragma unroll
-                    for (int j = 0; j < P; ++j) {
-                        const float g = (float)(nl[j] * wscale) * winv;
-                        if (g > 0.f) atomicAdd(grow + lab[j], (unsigned)(g * GFIX + 0.5f));
-                    }
-                    if (lane == 0) atomicAdd(grow + blank, (unsigned)((float)wbsum * winv * GFIX + 0.5f));
-                }
-            }
-            __syncwarp();
-            if (fail) break;
-            // tile epilogue: grad = p - occupancy (:139-145), coalesced row stores
-            for (int r = 0; r < rmax; ++r) {
-                const float zinv = __shfl_sync(0xffffffffu, my_Zinv, r);
-                float *orow = gbase + (int64_t)(t0 + r) * a.fs;
-                for (int k = lane; k < K; k += 32)
-                    orow[k] = te[r * Kp + k] * zinv - (float)tgu[r * Kp + k] * (1.f / GFIX);
-            }
-            __syncwarp();
-        }
+        fail = !beta_tiles<P, true>(a, c, q, c.ntiles - 1, 0, !short_utt, bb, bl, kscale);
     }
-
-    // ------------------------------------------------------------------ outputs
-    if (fail) {  // reference returns the zero-initialised grad on its failure path
-        for (int t = 0; t < T; ++t) {
-            float *orow = gbase + (int64_t)t * a.fs;
-            for (int k = lane; k < K; k += 32) orow[k] = 0.f;
-        }
-    }
-    for (int t = max(T, 0); t < a.Tmax; ++t) {  // padded frames carry no gradient
-        float *orow = gbase + (int64_t)t * a.fs;
-        for (int k = lane; k < K; k += 32) orow[k] = 0.f;
-    }
+    if (fail) zero_rows(a, c.gbase, 0, c.T, lane, 32);   // the reference returns the zero-initialised grad on its failure path
+    zero_rows(a, c.gbase, max(c.T, 0), a.Tmax, lane, 32);  // padded frames carry no gradient
     const float lz = warp_sum(logZ);
-    if (lane == 0) {
-        float nll;
-        if (short_utt && !fail) nll = CUDART_INF_F;
-        else nll = (float)(-(log(final_sum) - (double)S * 0.69314718055994530942 - (double)lz));
-        a.nll[u] = nll;
-        a.skip[u] = fail ? 1 : 0;
+    if (lane == 0) write_loss(a, u, short_utt, fail, final_sum, S, lz);
+}
+
+// Latency shape (few utterances, e.g. the 32 of a training step): TWO WARPS per utterance meet in the middle.
+// Warp 0 runs alpha forward, warp 1 beta backward, at the same time, each spilling its half of the trellis; after
+// one barrier warp 0 continues alpha through the second half combining with the stored beta sums, warp 1 continues
+// beta through the first half combining with the stored alpha: T dependent frame steps instead of 2T.
+template <int P>
+__global__ void __launch_bounds__(64) ctc_pair_kernel(CtcArgs a) {
+    extern __shared__ float smem[];
+    __shared__ int fail_flag;
+    const int lane = threadIdx.x & 31, role = threadIdx.x >> 5;
+    const int u = blockIdx.x;
+    WarpCtx c;
+    c.nbuf = 2; c.lane = lane;
+    c.te0 = smem + (size_t)role * 3 * TT * a.Kp;
+    c.tg = c.te0 + 2 * TT * a.Kp;
+    c.T = min(a.Tlen[u], a.Tmax);
+    c.ntiles = (c.T + TT - 1) / TT;
+    c.base = a.acts + (int64_t)u * a.us;
+    c.gbase = a.grad + (int64_t)u * a.us;
+    c.wsu = reinterpret_cast<double *>(a.ws) + (int64_t)u * a.ws_utt;
+    const int lo = a.loff[u];
+    LaneLabels<P> q;
+    q.load(a, lo, a.loff[u + 1] - lo, lane);
+    const bool short_utt = (c.T < q.nlab);
+    const bool recur = !short_utt && c.T > 0;
+    const int mid = c.ntiles / 2;          // tiles [0, mid): alpha spilled, beta combines; [mid, ntiles): the reverse
+    if (threadIdx.x == 0) fail_flag = (c.T <= 0) ? 1 : 0;
+    __syncthreads();
+
+    float logZ = 0.f;
+    int S = 0, kscale = 0;
+    double x0[P], x1[P];     // (ab, al) in warp 0, (bb, bl) in warp 1
+#pragma unroll
+    for (int j = 0; j < P; ++j) x0[j] = x1[j] = 0.0;
+    bool ok = true;
+    if (role == 0) {
+        if (lane == 0) x0[0] = 1.0;
+        if (recur) ok = alpha_tiles<P, false>(a, c, q, 0, mid, true, x0, x1, kscale, S, logZ);
+    } else {
+#pragma unroll
+        for (int j = 0; j < P; ++j)
+            if (lane * P + j == q.nlab) x0[j] = 1.0;
+        if (recur) ok = beta_tiles<P, false>(a, c, q, c.ntiles - 1, mid, true, x0, x1, kscale);
+    }
+    if (!ok && lane == 0) fail_flag = 1;
+    __threadfence_block();
+    __syncthreads();                       // both halves of the trellis are in the workspace
+    double final_sum = 1.0;
+    if (!fail_flag) {
+        if (role == 0) {
+            ok = alpha_tiles<P, true>(a, c, q, mid, c.ntiles, recur, x0, x1, kscale, S, logZ);
+            if (ok && recur) {
+                final_sum = final_mass<P>(q, lane, c.T, x0, x1);
+                if (!(final_sum > 0.0)) ok = false;
+            }
+        } else {
+            ok = beta_tiles<P, true>(a, c, q, mid - 1, 0, recur, x0, x1, kscale);
+        }
+        if (!ok && lane == 0) fail_flag = 1;
+    }
+    __syncthreads();
+    const bool fail = fail_flag != 0;
+    if (fail) zero_rows(a, c.gbase, 0, c.T, threadIdx.x, 64);
+    zero_rows(a, c.gbase, max(c.T, 0), a.Tmax, threadIdx.x, 64);
+    if (role == 0) {
+        // log Z of the first-half rows was only seen by warp 1's tiles: warp 0 walked tiles [0, mid) in its first
+        // phase and [mid, ntiles) in its second, i.e. every row exactly once
+        const float lz = warp_sum(logZ);
+        if (lane == 0) write_loss(a, u, short_utt, fail, final_sum, S, lz);
     }
 }
 
@@ -456,19 +652,42 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     a.grad = grad_out; a.nll = nll_out; a.skip = skip_out;
     a.ws = (float *)workspace; a.ws_utt = (int64_t)Tmax * 64 * P;
 
-    // many utterances: favour occupancy (one e tile); few: favour the latency of each warp (double-buffered tiles)
+    cudaStream_t st = (cudaStream_t)stream;
+    // few utterances (a training step): two warps per utterance meet in the middle of the trellis, one CTA each;
+    // CTCB_CTC=warp|pair forces a shape (tests)
+    static int shape_env = -1;
+    if (shape_env < 0) { const char *e = getenv("CTCB_CTC"); shape_env = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'p' ? 2 : 0)); }
+    const bool pair = (shape_env == 2) || (shape_env == 0 && B < 2 * num_sms());
+    if (pair) {
+        const size_t smem = (size_t)2 * 3 * TT * a.Kp * sizeof(float);
+        if (smem > 200 * 1024)
+            return set_error(CTCB_EINVAL, "ctcb_ctc_loss_grad_f32: K=%d too large for the shared-memory tile", K);
+        a.nbuf = 2;
+#define LAUNCH_PAIR(PP)                                                                                \
+    case PP: {                                                                                         \
+        CTCB_CUDA_CHECK(cudaFuncSetAttribute(ctc_pair_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ctc_pair_kernel<PP><<<B, 64, smem, st>>>(a);                                                   \
+        break;                                                                                         \
+    }
+        switch (P) {
+            LAUNCH_PAIR(1) LAUNCH_PAIR(2) LAUNCH_PAIR(4) LAUNCH_PAIR(8) LAUNCH_PAIR(16)
+            default: return set_error(CTCB_EINVAL, "bad P");
+        }
+#undef LAUNCH_PAIR
+        CTCB_LAUNCH_CHECK();
+        return CTCB_OK;
+    }
+    // many utterances: one warp each; favour occupancy (one e tile) when the SMs are full, else the latency of
+    // each warp (double-buffered tiles)
     a.nbuf = (B >= 16 * num_sms()) ? 1 : 2;
     const size_t per_warp = (size_t)(a.nbuf + 1) * TT * a.Kp * sizeof(float);
     int wpb = 8;
     while (wpb > 1 && per_warp * wpb > 100 * 1024) wpb >>= 1;
-    // small batches (the training step): spread the utterances over the SMs instead of packing 8 per CTA --
-    // each warp is a latency-bound serial chain and gains from an otherwise idle SM
     while (wpb > 1 && (B + wpb - 1) / wpb < 2 * num_sms()) wpb >>= 1;
     const size_t smem = per_warp * wpb;
     if (smem > 200 * 1024)
         return set_error(CTCB_EINVAL, "ctcb_ctc_loss_grad_f32: K=%d too large for the shared-memory tile", K);
     const int grid = (B + wpb - 1) / wpb;
-    cudaStream_t st = (cudaStream_t)stream;
 #define LAUNCH_P(PP)                                                                                   \
     case PP: {                                                                                         \
         CTCB_CUDA_CHECK(cudaFuncSetAttribute(ctc_warp_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \

@@ -165,3 +165,36 @@ def test_best_path_matches_reference_semantics(cuda):
     assert hyp == o_hyp and align == o_align
     q = np.zeros((10, 9)); q[[0, 3, 3, 0, 3, 1, 5, 5, 8], np.arange(9)] = 1.0
     assert ctc_fast.decode_best_path(np.asfortranarray(q)) == ([3, 3, 5], [2, 4, 7])
+
+
+def test_one_warp_shape_when_forced(cuda):
+    """Small batches take the two-warp meet-in-the-middle kernel; CTCB_CTC=warp forces the one-warp-per-utterance
+    kernel (the throughput shape of large batches) through the same golden / edge cases."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    root = os.path.dirname(here)
+    code = ("import os,sys; sys.path[:0]=[%r,%r,%r]; import pytest; "
+            "sys.exit(pytest.main(['-q','-p','no:cacheprovider','-k','golden_cases or ragged_batch or pairs_per_lane or fused_softmax', %r]))"
+            % (root, os.path.join(root, "stanford-ctc_b200"), here, os.path.abspath(__file__)))
+    env = dict(os.environ, CTCB_CTC="warp")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
+
+
+@pytest.mark.parametrize("T", [1, 3, 16, 17, 31, 32, 33, 47, 200])
+def test_meet_in_the_middle_tile_boundaries(T, cuda):
+    """Utterance lengths around the 16-frame tile size: 1 tile (no first half), odd/even tile counts."""
+    rng = np.random.RandomState(100 + T)
+    K = 20
+    nlab = max(1, min(T // 2, 6))
+    logits = rng.randn(K, T)
+    seq = (1 + rng.randint(0, K - 1, size=nlab)).astype(np.int32)
+    probs = recipes.softmax_cols(logits).astype(np.float32)
+    nll, grad, skip = _gpu_single(cuda, probs, seq)
+    o_nll, o_grad, o_skip = ctc_oracle.ctc_loss(np.asfortranarray(probs.astype(np.float64)), seq)
+    assert skip == o_skip
+    if not skip:
+        assert abs(nll - o_nll) / abs(o_nll) <= TOL
+        assert _rel(grad, o_grad) <= TOL
