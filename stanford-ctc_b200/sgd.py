@@ -46,6 +46,11 @@ class SGD:
         self.velocity = FlatList(model._views(self._vflat), self._vflat)
         self._gnorm2 = torch.zeros(1, dtype=torch.float32, device=model.dev)
         self._scratch = torch.zeros(8192, dtype=torch.uint8, device=model.dev)
+        # per-step log record {n_valid, sum nll, n_skipped, 0, gnorm^2, regcost, sweep error flag}: copied to pinned
+        # host memory on the stream right behind the step, read one step later (two slots alternate)
+        self._log_host = [torch.zeros(7, dtype=torch.float32).pin_memory() for _ in range(2)]
+        self._log_event = [torch.cuda.Event() for _ in range(2)]
+        self._log_slot = 0
 
         self.costt = []
         self.expcost = []
@@ -124,9 +129,11 @@ class SGD:
                     nframes=sum(d.shape[1] for d in datas))
 
     def _launch(self, prep, dist):
-        """Device side of one step (never synchronises)."""
+        """Device side of one step (never synchronises), followed on the stream by the copy of its log record."""
         m = self.model
+        torch = self._torch
         self.it += 1
+        prep["it"] = self.it
         mom = self._momentum_now()
         if prep["batch"] is not None:
             self.step_device(prep["batch"], mom)
@@ -139,12 +146,18 @@ class SGD:
             check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams, float(mom),
                                                  float(self.alpha), float(self.maxGNorm), ptr(self._gnorm2),
                                                  ptr(m.stats), st))
+        slot = self._log_slot
+        self._log_slot ^= 1
+        rec = torch.cat([m.stats, self._gnorm2, m._regcost, m._errflag.to(torch.float32)])
+        self._log_host[slot].copy_(rec, non_blocking=True)
+        self._log_event[slot].record()
+        prep["slot"] = slot
 
     def _finish(self, prep, rank):
-        """One small D2H per step for the log line, as the reference prints every iteration (sgd.py:113-167)."""
-        torch = self._torch
+        """The step's log line, as the reference prints every iteration (sgd.py:113-167), from its 28-byte record."""
         m = self.model
-        host = torch.cat([m.stats, self._gnorm2, m._regcost, m._errflag.to(torch.float32)]).cpu().numpy()
+        self._log_event[prep["slot"]].synchronize()
+        host = self._log_host[prep["slot"]].numpy().copy()
         if host[6] != 0:
             raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[6]))
         nvalid, costsum = float(host[0]), float(host[1])
@@ -169,13 +182,13 @@ class SGD:
                     self.regcost.append(rc)
         if self.verbose and rank == 0:
             print("Iter %d : Cost=%.4f, ExpCost=%.4f, GradNorm=%.4f, SeqLen=%d, NumFrames=%d."
-                  % (self.it, cost, self.expcost[-1] if self.expcost else float('nan'), gnorm,
+                  % (prep["it"], cost, self.expcost[-1] if self.expcost else float('nan'), gnorm,
                      prep["nlab"], prep["nframes"]))
 
     def run(self, data_dict, alis, keys, sizes):
         """Runs stochastic gradient descent with nesterov acceleration.  Model is objective.
-        Steps are software-pipelined: while the device works on minibatch i the host checks, packs and
-        uploads minibatch i+1 into the second staging buffer; the per-step log read-back follows."""
+        Steps are software-pipelined: while the device works on minibatch i the host checks, packs, uploads and
+        enqueues minibatch i+1 (second staging buffer); step i's log record is read after that."""
         dist, rank, world = self._world()
 
         # randomly select minibatch
@@ -185,14 +198,18 @@ class SGD:
         chunks = [keys[k0:k0 + step] for k0 in range(0, len(keys), step)]
         if not chunks:
             return
-        prep = self._prepare(data_dict, alis, chunks[0], rank, world)
+        # the host is always one step ahead of the device: step i+1 is packed, uploaded and enqueued while step i
+        # runs; only then is step i's log record awaited
+        pending = None
         for i in range(len(chunks)):
+            prep = self._prepare(data_dict, alis, chunks[i], rank, world)
             active = (prep["batch"] is not None) or world > 1
             if active:
                 self._launch(prep, dist)
             else:
                 self.it += 1               # the reference counts skipped utterances too (sgd.py:71)
-            nxt = self._prepare(data_dict, alis, chunks[i + 1], rank, world) if i + 1 < len(chunks) else None
-            if active:
-                self._finish(prep, rank)
-            prep = nxt
+            if pending is not None:
+                self._finish(pending, rank)
+            pending = prep if active else None
+        if pending is not None:
+            self._finish(pending, rank)
