@@ -346,7 +346,7 @@ static int make_map(CUtensorMap *m, const float *ptr, int rows, int K, int64_t l
 
 static inline int64_t pad4(int64_t x) { return (x + 3) / 4 * 4; }
 
-static int tc_pick_bn(int M, int N) {
+static int tc_pick_bn(int M, int N, int K) {
     static int force = -1;
     if (force < 0) { const char *e = getenv("CTCB_GEMM_BN"); force = e ? atoi(e) : 0; }
     if (force == 64 || force == 128 || force == 256) return force;
@@ -354,6 +354,9 @@ static int tc_pick_bn(int M, int N) {
     // measured (tools/gemm_rate.py): 256-wide tiles win once they still fill >= 2 waves of CTAs (16384x2048x2048:
     // 192 vs 163 TFLOP/s fp32-equivalent) and lose on small problems (6400x512x512: 0.062 vs 0.048 ms)
     if (N >= 256 && (int64_t)((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= 2 * num_sms()) return 256;
+    // reduction-heavy shapes (the weight gradients: 512 x 512 outputs over K = T*B rows) are split over K anyway;
+    // wide tiles halve the B-operand traffic per CTA (C2 step: 0.16 -> 0.14 ms for the two recurrent gradients)
+    if (N >= 256 && M <= 1024 && K >= 4096) return 256;
     return 128;
 }
 
@@ -384,7 +387,7 @@ bool gemm_tc_eligible(int M, int N, int K) { return gemm_tc_enabled() && M >= 64
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
     const int64_t Kp = pad4(K);
     size_t prep = ((size_t)M * Kp + (size_t)N * Kp) * sizeof(float);     // re-laid-out copies of A and B (when needed)
-    const int BN = tc_pick_bn(M, N);
+    const int BN = tc_pick_bn(M, N, K);
     const int splits = tc_choose_splits(M, N, K, BN);
     size_t part = splits > 1 ? (size_t)splits * M * N * sizeof(float) : 0;
     return align_up(prep, 256) + align_up(part, 256) + 1024;
@@ -439,7 +442,7 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
         Buse = Bhi; ldb_use = Kp;
     }
 
-    const int BN = tc_pick_bn(M, N);
+    const int BN = tc_pick_bn(M, N, K);
     int splits = tc_choose_splits(M, N, K, BN);
     const int nkb = (K + TC_BK - 1) / TC_BK;
     GemmTcArgs g;

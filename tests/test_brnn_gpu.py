@@ -33,7 +33,8 @@ def test_gemm_all_layouts_vs_numpy(cuda):
     torch = cuda
     rng = np.random.RandomState(0)
     ws = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
-    for (M, N, K) in [(300, 62, 41), (257, 130, 19), (128, 128, 4096), (64, 512, 20000), (1, 7, 3), (513, 512, 512)]:
+    for (M, N, K) in [(300, 62, 41), (257, 130, 19), (128, 128, 4096), (64, 512, 20000), (1, 7, 3), (513, 512, 512),
+                      (6400, 512, 62), (640, 512, 41), (200, 40, 32), (129, 33, 33)]:
         for ta in (0, 1):
             for tb in (0, 1):
                 A = rng.randn(*((K, M) if ta else (M, K))).astype(np.float32)

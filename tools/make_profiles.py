@@ -15,11 +15,12 @@ WANT = ['gpu__time_duration.sum', 'launch__grid_size', 'launch__block_size', 'la
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active', 'launch__occupancy_limit_shared_mem',
         'launch__occupancy_limit_registers']
-reps = [r for r in ("prof_ctc_r1b", "prof_gemmtc_r1", "prof_sweepv3_r1", "prof_sweep_r1") if os.path.exists(os.path.join(G, r + ".ncu-rep"))]
+reps = [r for r in ("prof_ctc_r1b", "prof_ctcpair_r1", "prof_gemmtc_r1", "prof_sweepcl_r1", "prof_sweep_r1") if os.path.exists(os.path.join(G, r + ".ncu-rep"))]
 traffic = {}
 with open(os.path.join(P, "ncu_%s_summary.txt" % tag), "w") as f:
     f.write("ncu --set full --clock-control none --import-source on captures on B200 (sm_100a), one launch each:\n"
             "  -k regex:ctc_warp -s 1 -c 1       python tools/prof_ctc.py                                   (B=8192 x C1 shape, 814 MB > L2)\n"
+            "  -k regex:ctc_pair -s 1 -c 1       python bench.py --steps 2 --warmup 1 --no-cpu-baseline      (inside the C2 step, B=32)\n"
             "  -k regex:gemm_tc_kernel -s 6 -c 2 python bench.py --steps 2 --warmup 1 --no-cpu-baseline      (inside the C2 step)\n"
             "  -k regex:sweep_cluster -s 2 -c 1  python bench.py --steps 2 --warmup 1 --no-cpu-baseline      (inside the C2 step)\n"
             "  -k regex:sweep_kernel  -s 2 -c 1  (general counter-barrier kernel, captured before the cluster kernel became the default)\n\n")
@@ -40,8 +41,8 @@ with open(os.path.join(P, "ncu_%s_summary.txt" % tag), "w") as f:
             f.write("\n")
     f.write("SASS evidence (cuobjdump -sass stanford-ctc_b200/libctcb200.so):\n"
             "  gemm_tc_kernel           UTCHMMA (tcgen05.mma), UTMALDG.2D (TMA), LDTM.x32 (tcgen05.ld), UTCBAR (tcgen05.commit)\n"
-            "  sweep_cluster_kernel*    UBLKCP.S.S (cp.async.bulk smem -> cluster smem), SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier), FFMA2\n"
-            "  ctc_warp_kernel          LDGSTS (cp.async), REDUX / CREDUX, DADD / DMUL, ATOMS.ADD\n")
+            "  sweep_cluster_kernel     STAS (st.async into cluster shared memory), SYNCS.PHASECHK.TRANS64.TRYWAIT (mbarrier), FFMA2\n"
+            "  ctc_warp/ctc_pair_kernel LDGSTS (cp.async), REDUX / CREDUX, DADD / DMUL, ATOMS.ADD\n")
 json.dump(traffic, open(os.path.join(P, "ncu_traffic_%s.json" % tag), "w"), indent=1)
 
 rows = [r for r in csv.reader(open(os.path.join(G, "launches_%s.csv" % tag))) if len(r) > 5]
