@@ -657,9 +657,14 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     // CTCB_CTC=warp|pair forces a shape (tests)
     static int shape_env = -1;
     if (shape_env < 0) { const char *e = getenv("CTCB_CTC"); shape_env = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'p' ? 2 : 0)); }
-    const bool pair = (shape_env == 2) || (shape_env == 0 && B < 2 * num_sms());
+    // the two-warp shape wins as long as its CTAs (one per utterance) fit the SMs in one wave: below that the
+    // one-warp shape leaves the schedulers short of warps (C5 sweep: 1.6 vs 3.1 ms at T=2000, B=292 vs 604)
+    const size_t smem_pair = (size_t)2 * 3 * TT * a.Kp * sizeof(float);
+    int pair_per_sm = (int)((200 * 1024) / (smem_pair ? smem_pair : 1));
+    if (pair_per_sm > 8) pair_per_sm = 8;
+    const bool pair = (shape_env == 2) || (shape_env == 0 && pair_per_sm >= 1 && B <= pair_per_sm * num_sms());
     if (pair) {
-        const size_t smem = (size_t)2 * 3 * TT * a.Kp * sizeof(float);
+        const size_t smem = smem_pair;
         if (smem > 200 * 1024)
             return set_error(CTCB_EINVAL, "ctcb_ctc_loss_grad_f32: K=%d too large for the shared-memory tile", K);
         a.nbuf = 2;

@@ -39,7 +39,7 @@ for T in (100, 500, 2000, 5000):
             gbs = B * alg_per / ms / 1e6
             rows.append(dict(T=T, L=L, K=K, B=B, ms=round(ms, 3), utt_per_s=round(B / ms * 1e3), alg_GBs=round(gbs, 1),
                              frac_hbm=round(gbs / peaks["hbm_gbs"], 4), act_MB=round(B * alg_per / 2e6, 1), skips=int(skip.sum()),
-                             shape="two warps per utterance" if B < 2 * torch.cuda.get_device_properties(0).multi_processor_count else "one warp per utterance"))
+                             shape="two warps per utterance" if B <= min(8, (200 * 1024) // (384 * ((K + 29) // 32 * 32 + 2))) * torch.cuda.get_device_properties(0).multi_processor_count else "one warp per utterance"))
             print(rows[-1], flush=True)
             del acts, grad, ws
             torch.cuda.empty_cache()
