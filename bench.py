@@ -69,7 +69,7 @@ def make_batch(c, n_utts, seed):
 _W = {}
 
 
-def _ref_worker_init(cfg, shared_params, nparams, blas_threads):
+def _ref_worker_init(cfg, shared_params, nparams, blas_threads, shared_grads):
     from oracle import brnn_oracle
     try:
         from threadpoolctl import threadpool_limits
@@ -82,6 +82,7 @@ def _ref_worker_init(cfg, shared_params, nparams, blas_threads):
     nn.initParams()
     _W["nn"] = nn
     _W["params"] = np.frombuffer(shared_params, dtype=np.float64, count=nparams)
+    _W["grads"] = np.frombuffer(shared_grads, dtype=np.float64).reshape(-1, nparams)   # one row per task slot
     _W["cfg"] = cfg
 
 
@@ -97,12 +98,13 @@ def _unflatten_into(flat, stack):
 
 
 def _ref_worker_step(task):
-    seed, count = task
+    seed, count, slot = task
     nn = _W["nn"]
     _unflatten_into(_W["params"], nn.stack)
     datas, labels = make_batch(_W["cfg"], count, seed)
     costs, grad, skips = nn.costAndGradBatch(datas, labels)
-    return _flatten(grad), float(costs[~skips].sum()), int(np.sum(~skips))
+    _W["grads"][slot, :] = _flatten(grad)          # shared memory: nothing but two scalars goes through the pipe
+    return float(costs[~skips].sum()), int(np.sum(~skips))
 
 
 def run_reference(args, c):
@@ -130,21 +132,33 @@ def run_reference(args, c):
     sp = np.frombuffer(shared, dtype=np.float64, count=flat.size)
     sp[:] = flat
     vel = np.zeros_like(flat)
+    gshared = mp.RawArray("d", workers * flat.size)
+    gmat = np.frombuffer(gshared, dtype=np.float64).reshape(workers, flat.size)
     ctx = mp.get_context("fork")
-    pool = ctx.Pool(workers, initializer=_ref_worker_init, initargs=(c, shared, flat.size, blas))
+    pool = ctx.Pool(workers, initializer=_ref_worker_init, initargs=(c, shared, flat.size, blas, gshared))
+    try:
+        from threadpoolctl import threadpool_limits as _tl
+    except Exception:
+        _tl = None
     # utterances of a step split as evenly as possible over the workers
     counts = [B // workers + (1 if i < B % workers else 0) for i in range(workers)]
 
     def step(it):
         mom = 0.5 if it <= 10 else 0.9
         sp[:] = flat + mom * vel                                 # sgd.py:91-93 look-ahead
-        res = pool.map(_ref_worker_step, [(1000 * it + i, n) for i, n in enumerate(counts) if n > 0])
-        g = np.sum([r[0] for r in res], axis=0)
+        tasks = [(1000 * it + i, n, i) for i, n in enumerate(counts) if n > 0]
+        res = pool.map(_ref_worker_step, tasks, chunksize=1)
+        ones = np.ones(len(tasks))
+        if _tl is not None:                                      # the reduction over workers on all cores (gemv)
+            with _tl(limits=ncores):
+                g = ones @ gmat[:len(tasks)]
+        else:
+            g = ones @ gmat[:len(tasks)]
         gnorm = np.sqrt(np.sum(g * g))
         alph = 1e-5 * min(1.0, 1500.0 / gnorm) if gnorm > 0 else 1e-5
         vel[:] = mom * vel - alph * g                            # sgd.py:130-140
         flat[:] = flat + vel                                     # sgd.py:161
-        return sum(r[1] for r in res) / max(1, sum(r[2] for r in res))
+        return sum(r[0] for r in res) / max(1, sum(r[1] for r in res))
 
     for it in range(1, args.warmup + 1):
         step(it)
@@ -155,10 +169,23 @@ def run_reference(args, c):
     dt = time.perf_counter() - t0
     pool.close()
     value = B * args.steps / dt
+    # the reference as it ships is single-threaded, one utterance per step (sgd.py:70-161): time that too
+    single = None
+    try:
+        from threadpoolctl import threadpool_limits
+        datas, labels = make_batch(c, 2, 7)
+        with threadpool_limits(limits=1):
+            nn.costAndGrad(datas[0], labels[0])
+            t1 = time.perf_counter()
+            for d_, l_ in zip(datas, labels):
+                nn.costAndGrad(d_, l_)
+            single = len(datas) / (time.perf_counter() - t1)
+    except Exception:
+        single = None
     kind = "port"
     sample = ("%d full steps of the workload (B=%d utterances each, T=%d); BRNN = float64 NumPy restatement "
               "(oracle/brnn_oracle.py, as the reference's rnnetcpu.py), CTC = %s; %d worker processes x %d BLAS "
-              "thread(s)" % (args.steps, B, c["T"],
+              "thread(s), gradients summed through shared memory" % (args.steps, B, c["T"],
                              "unmodified reference ctc_fast.pyx (oracle/_ref)" if ctc_oracle.ref_module() is not None
                              else "C restatement oracle/ctc_oracle.c", workers, blas))
     line = {
@@ -168,7 +195,7 @@ def run_reference(args, c):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": c["name"], "global_batch": B, "last_cost": cost},
         "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": workers * blas, "kind": kind,
-                         "sample": sample},
+                         "sample": sample, "single_core_value": single},
         "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
