@@ -121,8 +121,18 @@ def run_reference(args, c):
         ncores = len(os.sched_getaffinity(0))
     except Exception:
         ncores = os.cpu_count() or 1
-    workers = max(1, min(ncores, B))
-    blas = max(1, ncores // workers)
+    # a container may be given fewer CPUs than it can see (cgroup quota): more workers than that only thrash
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            ncores = max(1, min(ncores, int(int(q) / int(per))))
+    except Exception:
+        pass
+    # one single-threaded worker per core: the per-frame products are too small for BLAS threads (measured on the
+    # GPU host, 16-CPU quota: 16 x 1 threads 112 utt/s, 32 x 1 110, 16 x 8 52, 32 x 4 43);
+    # CTCB_REF_WORKERS / CTCB_REF_BLAS override for experiments
+    workers = max(1, min(ncores, B, int(os.environ.get("CTCB_REF_WORKERS", "1000000"))))
+    blas = max(1, int(os.environ.get("CTCB_REF_BLAS", "1")))
     np.random.seed(33)
     nn = brnn_oracle.NNet(c["D"], c["K"], c["H"], c["N"], c["T"], temporalLayer=c["tl"], dtype=np.float64,
                           allow_top_temporal=c.get("top", False))
