@@ -80,17 +80,19 @@ __device__ __forceinline__ void ffma2(unsigned long long &d, unsigned long long 
 // The kernel: 16 warps per CTA, 64 output units per CTA, CS = H/64 CTAs per cluster, NB
 // utterances per cluster.  The INPUT dimension is split over the warps, not over the lanes: warp w owns input
 // units [w*H/16, (w+1)*H/16) of all 64 output units; lane l owns output units 2l, 2l+1 (H/8 weights per thread
-// in registers, packed as FFMA2 operands over input pairs).  Per warp and step at H = 512, NB = 5:
+// in registers, one 64-bit register pair per input unit: the FFMA2 form (pair of units) x (scalar state)).
+// Per warp and step at H = 512, NB = 5:
 //   * every lane needs the same slice of the previous state: 40 broadcast LDS.128;
 //   * no shuffle reduction: a lane's accumulators are complete over its warp's slice; the 16 per-warp partial
-//     sums of an output meet in shared memory (one extra CTA barrier), where thread (utterance, unit) adds
-//     them, applies clip/mask, stores the state to HBM and stages it for the push to the CS peers.
-//   block layout (NB*256 B per CTA and step): [utterance][unit 64]
-// Measured (tools/sweep_time.py, T = 200, B = 32): 1.85 us/step at H = 512 (lane-split predecessor with a
-// 31-shuffle butterfly: 2.3), 0.77 at H = 256 (1.3).  Cost model from B = 4..32: 0.65 us fixed (barrier wait,
-// two CTA barriers, DSMEM push) + 0.25 us per utterance of the cluster = 32768 FMA per SM at 64 FMA/clk: B200
-// issues a register-operand FFMA/FFMA2 warp instruction at half rate, so the FMA pipe -- not shared memory,
-// which variants with 4 or 8 units per thread and 2-4x fewer LDS confirmed by being no faster -- is the floor.
+//     sums of an output meet in shared memory (the one CTA barrier of the step), where thread (utterance, unit)
+//     adds them, applies clip/mask, stores the state to HBM and sends it to the CS peers with st.async.
+//   state layout in every CTA: [buffer 2][source CTA][utterance][unit 64]
+// Measured (tools/sweep_time.py, T = 200, B = 32): 1.76 us/step at H = 512 (lane-split predecessor with a
+// 31-shuffle butterfly: 2.3; this kernel with a cp.async.bulk push and a second barrier: 1.85), 0.65 at H = 256,
+// 0.43 at H = 128.  Cost model from B = 4..32 at H = 512: 0.4 us fixed (wait, barrier, reduction, exchange) +
+// 0.27 us per utterance of the cluster, of which 0.2 us is 32768 FMA per SM at the measured FFMA2 rate (2.8
+// cycles per warp instruction and sub-partition, tools/micro/mma_rate.cu).  ncu (profiles/): FMA pipe 41 % of
+// active cycles, issue slots 39 %; stall samples mostly math-pipe throttle and the mbarrier wait.
 // ---------------------------------------------------------------------------------------------------
 template <int KI, int NB>
 __global__ void __launch_bounds__(512, 1) sweep_cluster_kernel(SweepClusterArgs a) {

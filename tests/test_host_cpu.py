@@ -112,3 +112,33 @@ def test_data_parallel_reduction_world2_gloo():
                           [np.array([5.0, costs.sum(), 0.0, 0.0])])
     assert np.array_equal(res[0], res[1])                 # identical on every rank
     np.testing.assert_allclose(res[0], full, rtol=1e-12, atol=1e-12)
+
+
+def test_bench_reference_arm_json_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside ours) prints one JSON line with the
+    contract's keys, runs the oracle port on host cores only and needs no GPU."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")}
+    env["CTCB_REF_WORKERS"] = "2"
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "1",
+                        "--steps", "1", "--warmup", "0", "--config", "tiny"], env=env, capture_output=True, text=True,
+                       timeout=300)
+    assert r.returncode == 0, r.stderr[-1500:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e", "gpu_launches"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["cores"] == 2
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # a non-zero rank of a multi-GPU launch exits silently
+    env2 = dict(env, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r2 = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--gpus", "2",
+                         "--steps", "1", "--warmup", "0", "--config", "tiny"], env=env2, capture_output=True, text=True,
+                        timeout=300)
+    assert r2.returncode == 0 and not [l for l in r2.stdout.splitlines() if l.startswith("{")]
