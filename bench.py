@@ -170,6 +170,19 @@ def run_reference(args, c):
         flat[:] = flat + vel                                     # sgd.py:161
         return sum(r[0] for r in res) / max(1, sum(r[1] for r in res))
 
+    # Bounded sample: a step of this arm processes n_s <= B utterances of the step's minibatch (utterances are
+    # independent, so the rate does not depend on n_s), sized from one probe step so that the warm-up and the timed
+    # steps together stay within ~2 minutes of host time whatever K, W and N the driver passes.
+    t_probe = time.perf_counter()
+    step(0)
+    t_step = time.perf_counter() - t_probe
+    budget = float(os.environ.get("CTCB_REF_BUDGET_S", "120"))
+    n_s = B
+    total_steps = max(1, args.steps + args.warmup)
+    if t_step * total_steps > budget:
+        n_s = int(B * budget / (t_step * total_steps))
+        n_s = max(workers, min(B, n_s // workers * workers))
+        counts = [n_s // workers + (1 if i < n_s % workers else 0) for i in range(workers)]
     for it in range(1, args.warmup + 1):
         step(it)
     t0 = time.perf_counter()
@@ -178,7 +191,7 @@ def run_reference(args, c):
         cost = step(it)
     dt = time.perf_counter() - t0
     pool.close()
-    value = B * args.steps / dt
+    value = n_s * args.steps / dt
     # the reference as it ships is single-threaded, one utterance per step (sgd.py:70-161): time that too
     single = None
     try:
@@ -193,9 +206,9 @@ def run_reference(args, c):
     except Exception:
         single = None
     kind = "port"
-    sample = ("%d full steps of the workload (B=%d utterances each, T=%d); BRNN = float64 NumPy restatement "
+    sample = ("%d steps of %d of the workload's B=%d utterances per step, T=%d; BRNN = float64 NumPy restatement "
               "(oracle/brnn_oracle.py, as the reference's rnnetcpu.py), CTC = %s; %d worker processes x %d BLAS "
-              "thread(s), gradients summed through shared memory" % (args.steps, B, c["T"],
+              "thread(s), gradients summed through shared memory" % (args.steps, n_s, B, c["T"],
                              "unmodified reference ctc_fast.pyx (oracle/_ref)" if ctc_oracle.ref_module() is not None
                              else "C restatement oracle/ctc_oracle.c", workers, blas))
     line = {
@@ -203,7 +216,7 @@ def run_reference(args, c):
         "unit": "utterances/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": c["name"], "global_batch": B, "last_cost": cost},
+        "config": {"workload": c["name"], "global_batch": B, "utterances_per_timed_step": n_s, "last_cost": cost},
         "cpu_baseline": {"value": value, "unit": "utterances/s", "cores": workers * blas, "kind": kind,
                          "sample": sample, "single_core_value": single},
         "e2e": {"value": value, "unit": "utterances/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
