@@ -187,3 +187,57 @@ def test_rnn_variants_match_golden(golden_rnn):
         for i, (dw, db) in enumerate(grad):
             np.testing.assert_allclose(dw, golden_rnn["%s/dw%d" % (tag, i)], rtol=1e-9, atol=1e-12)
     assert int(golden_rnn["uni/clip_hits"]) > 0
+
+
+# ---- randomised pinning of the restatements against the compiled reference modules ---------------------------
+@pytest.mark.skipif(ctc_oracle.ref_module() is None, reason="oracle/_ref not built")
+def test_c_restatement_equals_reference_on_random_shapes():
+    """300 random (K, T, |l|) cases incl. T = 1, T = |l|, T < |l|, heavy label repetition and peaked
+    distributions: the C restatement must agree with the unmodified ctc_fast.pyx bit for bit (same float64
+    operation order), skip flags included."""
+    rng = np.random.RandomState(2024)
+    n_skip = n_inf = 0
+    for case in range(300):
+        K = int(rng.randint(2, 40))
+        T = int(rng.choice([1, 2, 3, 5, 8, 17, 40, 90]))
+        nlab = int(rng.randint(1, max(2, min(T + 3, 25))))
+        scale = float(rng.choice([0.5, 1.0, 4.0, 12.0]))
+        probs = recipes.softmax_cols(rng.randn(K, T) * scale).astype(np.float32).astype(np.float64)
+        if rng.rand() < 0.3:
+            seq = np.full(nlab, 1 + rng.randint(K - 1), dtype=np.int32)           # one label repeated
+        else:
+            seq = (1 + rng.randint(0, K - 1, size=nlab)).astype(np.int32)
+        p = np.asfortranarray(probs)
+        nll, grad, skip = ctc_oracle.ctc_loss(p, seq)
+        r_nll, r_grad, r_skip = ctc_oracle.ref_ctc_loss(p, seq)
+        assert skip == r_skip, (case, K, T, nlab)
+        n_skip += skip
+        if skip:
+            continue
+        if np.isinf(r_nll):
+            n_inf += 1
+            assert np.isinf(nll)
+        else:
+            assert nll == r_nll, (case, K, T, nlab, nll, r_nll)
+        assert np.array_equal(grad, r_grad), (case, K, T, nlab)
+    assert n_skip > 0 and n_inf > 0          # the sample did reach the failure and the T < |l| paths
+
+
+@pytest.mark.skipif(ctc_oracle.ref_module("ctc_fast_blankforce") is None, reason="oracle/_ref not built")
+def test_blankforce_restatement_equals_reference_on_random_shapes():
+    rng = np.random.RandomState(77)
+    for case in range(200):
+        K = int(rng.randint(2, 30))
+        T = int(rng.choice([1, 2, 4, 9, 33, 70]))
+        L = int(rng.randint(1, 20))
+        probs = recipes.softmax_cols(rng.randn(K, T) * float(rng.choice([1.0, 5.0]))).astype(np.float32).astype(np.float64)
+        seq = rng.randint(0, K, size=L).astype(np.int32)
+        if rng.rand() < 0.7:
+            seq[::2] = 0                                                           # the usual interleaved blanks
+        p = np.asfortranarray(probs)
+        nll, grad, skip = ctc_oracle.ctc_loss_blankforce(p, seq)
+        r_nll, r_grad, r_skip = ctc_oracle.ref_ctc_loss_blankforce(p, seq)
+        assert skip == r_skip, (case, K, T, L)
+        if not skip:
+            assert (nll == r_nll) or (np.isnan(nll) and np.isnan(r_nll)) or (np.isinf(nll) and np.isinf(r_nll)), (case, nll, r_nll)
+            assert np.array_equal(grad, r_grad, equal_nan=True), (case, K, T, L)
