@@ -491,7 +491,7 @@ def run_ours(args, c):
                        "parallelism": "dp%d" % world, "l2": "flushed between timed steps (256 MiB write, untimed)",
                        "optimizer": "nesterov, maxGradNorm=1500, step=1e-5",
                        "flops_per_utt": flops_per_utt(c)},
-            "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 24,
+            "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 28,
                     "api": "sgd.SGD.run(data_dict, alis, keys, sizes) with host arrays", "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall,
             "model_tflops": value * flops_per_utt(c) / 1e12,
