@@ -15,6 +15,27 @@ def shard(items, rank, world):
     return list(items[rank::world])
 
 
+def select_step_utterances(data_dict, alis, chunk, max_frames, rank, world, log=None):
+    """The utterances of one step that THIS rank computes.  The reference's per-utterance admission rules
+    (sgd.py:76-88: skip when longer than the buffers, skip when there are fewer frames than labels) are applied
+    to the whole step in the same order on every rank -- two cheap length look-ups per key -- and only then is
+    the list sharded, so all ranks agree on the shards without looking at each other's data."""
+    used = []
+    for k in chunk:
+        nframes = data_dict[k].shape[1]
+        if nframes > max_frames:
+            if log:
+                log("SKIPPING utt exceeds batch length (Utterance length %d)." % nframes)
+            continue
+        nlab = len(alis[k])
+        if nframes < nlab:
+            if log:
+                log("SKIPPING utt frames less than label length (Utterance length %d, Num Labels %d)." % (nframes, nlab))
+            continue
+        used.append(k)
+    return shard(used, rank, world)
+
+
 def per_rank_capacity(batch_size, world):
     """Utterance capacity each rank must allocate for a global step of batch_size utterances."""
     return (batch_size + world - 1) // max(world, 1)

@@ -106,22 +106,9 @@ class SGD:
         """Host side of one step: the reference's length checks (sgd.py:76-88), sharding over ranks, packing into
         the idle staging buffer and the asynchronous H2D copy."""
         m = self.model
-        datas, labels, used = [], [], []
-        for k in chunk:
-            mb_data = data_dict[k]
-            if mb_data.shape[1] > self.maxBatch:
-                logging.info("SKIPPING utt exceeds batch length (Utterance length %d)." % mb_data.shape[1])
-                continue
-            mb_labels = np.array(alis[k], dtype=np.int32)
-            if mb_data.shape[1] < mb_labels.shape[0]:
-                logging.info("SKIPPING utt frames less than label length "
-                             "(Utterance length %d, Num Labels %d)." % (mb_data.shape[1], mb_labels.shape[0]))
-                continue
-            datas.append(mb_data)
-            labels.append(mb_labels)
-            used.append(k)
-        if world > 1:          # shard the step's utterances over the ranks
-            datas, labels, used = (parallel.shard(x, rank, world) for x in (datas, labels, used))
+        used = parallel.select_step_utterances(data_dict, alis, chunk, self.maxBatch, rank, world, log=logging.info)
+        datas = [data_dict[k] for k in used]
+        labels = [np.array(alis[k], dtype=np.int32) for k in used]     # only this rank's utterances are converted
         batch = None
         if datas:
             batch = m.swap_batches().pack(datas, labels).upload()

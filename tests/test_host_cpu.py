@@ -142,3 +142,25 @@ def test_bench_reference_arm_json_contract():
                          "--steps", "1", "--warmup", "0", "--config", "tiny"], env=env2, capture_output=True, text=True,
                         timeout=300)
     assert r2.returncode == 0 and not [l for l in r2.stdout.splitlines() if l.startswith("{")]
+
+
+def test_step_utterance_selection_is_consistent_across_ranks():
+    """sgd.py:76-88 admission rules, then round-robin sharding: every admitted utterance is owned by exactly one
+    rank, skipped ones by none, and all ranks log the same skips."""
+    import parallel
+    rng = np.random.RandomState(0)
+    keys = ["k%d" % i for i in range(23)]
+    data = {k: np.zeros((5, int(rng.randint(3, 60))), dtype=np.float32) for k in keys}
+    alis = {k: list(range(int(rng.randint(1, 20)))) for k in keys}
+    data["k3"] = np.zeros((5, 80), dtype=np.float32)          # longer than the buffers
+    alis["k7"] = list(range(data["k7"].shape[1] + 1))         # more labels than frames
+    ok = [k for k in keys if data[k].shape[1] <= 64 and data[k].shape[1] >= len(alis[k])]
+    assert "k3" not in ok and "k7" not in ok
+    for world in (1, 2, 3, 8):
+        logs = [[] for _ in range(world)]
+        shards = [parallel.select_step_utterances(data, alis, keys, 64, r, world, log=logs[r].append) for r in range(world)]
+        assert sorted(sum(shards, [])) == sorted(ok)
+        assert max(len(s) for s in shards) - min(len(s) for s in shards) <= 1
+        assert shards[0] == ok[0::world]
+        assert all(l == logs[0] for l in logs) and len(logs[0]) == len(keys) - len(ok)
+        assert any("exceeds batch length" in m for m in logs[0]) and any("less than label length" in m for m in logs[0])
