@@ -27,6 +27,12 @@ def golden_brnn():
 
 
 @pytest.fixture(scope="session")
+def golden_rnnetcpu():
+    import numpy as np
+    return np.load(os.path.join(ROOT, "tests", "golden", "rnnetcpu_ref.npz"))
+
+
+@pytest.fixture(scope="session")
 def golden_bf():
     import numpy as np
     return np.load(os.path.join(ROOT, "tests", "golden", "blankforce_cases.npz"))

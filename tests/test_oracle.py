@@ -83,6 +83,45 @@ def test_brnn_restatement_matches_golden(golden_brnn):
         np.testing.assert_allclose(dw, golden_brnn["rnnetcpu/dw%d" % i], rtol=1e-9, atol=1e-12)
 
 
+# ---- the BRNN restatement pinned to the reference's own NumPy BRNN (debug-utils/rnnetcpu.py) -----------------
+RNNETCPU_CASES = ["selftest", "tl1_of_2", "tl3_of_5", "no_temporal", "long_T"]
+
+
+@pytest.mark.parametrize("name", RNNETCPU_CASES)
+def test_brnn_restatement_pinned_to_reference_rnnetcpu(name, golden_rnnetcpu):
+    """tests/golden/rnnetcpu_ref.npz holds inputs and outputs of the REFERENCE's rnnetcpu.RNNet.costAndGrad
+    (rnnetcpu.py:54-150), produced by tests/golden/gen_rnnetcpu_ref.py from the file as it lies in
+    /root/reference (print/xrange/tabs converted mechanically, CTC = the unmodified ctc_fast.pyx).  The
+    restatement, configured as that file computes -- float64 weights as drawn, no 20.0 clip (rnnetcpu.py:82-90),
+    no float32 hand-offs, no L2 -- must reproduce cost and every gradient to 1e-12."""
+    g = golden_rnnetcpu
+    seed, D, T, K, H, N, tl = (int(x) for x in g[name + "/cfg"])
+    nn = brnn_oracle.NNet(D, K, H, N, T, temporalLayer=tl, dtype=np.float64, round_f32=False)
+    np.random.seed(seed); np.random.randn(D, T)                     # same global stream position as the reference
+    nn.initParams()
+    assert len(nn.stack) == int(g[name + "/nstack"])
+    for i, (w, b) in enumerate(nn.stack):                           # same shapes and np.random draw order ...
+        assert np.array_equal(w, g["%s/w%d" % (name, i)].astype(np.float32).astype(np.float64))
+        w[...] = g["%s/w%d" % (name, i)]                            # ... then the reference's un-rounded float64 values
+        b[...] = g["%s/b%d" % (name, i)]
+    nn.maxAct = np.inf                                              # rnnetcpu.py has no clip
+    cost, grad, skip = nn.costAndGrad(g[name + "/data"], g[name + "/labels"])
+    assert not skip
+    ref = float(g[name + "/cost"])
+    assert abs(cost - ref) <= 1e-12 * abs(ref), (cost, ref)
+    for i, (dw, db) in enumerate(grad):
+        rdw = g["%s/dw%d" % (name, i)]
+        assert np.abs(dw - rdw).max() <= 1e-12 * max(1.0, np.abs(rdw).max()), i
+        if i <= N:
+            rdb = g["%s/db%d" % (name, i)]
+            assert np.abs(db - rdb).max() <= 1e-12 * max(1.0, np.abs(rdb).max()), i
+
+
+def test_reference_selftest_known_answer(golden_rnnetcpu):
+    """`COST 12.023458823` is what the reference's own `python rnnetcpu.py` prints (rnnetcpu.py:180-193)."""
+    assert abs(float(golden_rnnetcpu["selftest/cost"]) - 12.023458823) < 5e-10
+
+
 def test_brnn_restatement_gradcheck():
     """Finite-difference check of the restatement itself (tolerance of the reference's own check,
     |analytic - numeric| <= 1e-4: rnnetcpu.py:165, ctc/gradcheck.py:40)."""
