@@ -27,6 +27,9 @@ extern "C" {
 #define CTCB_ECUDA (-2)    /* CUDA runtime error (see ctcb_last_error) */
 #define CTCB_ENOMEM (-3)   /* caller workspace too small */
 
+/* Longest label sequence per utterance the CTC kernel accepts (16 state pairs per lane, ctc.cu). */
+#define CTCB_CTC_MAX_LABELS 511
+
 /* ---- library ------------------------------------------------------------------------------ */
 int ctcb_version(void);
 const char *ctcb_last_error(void);
@@ -134,7 +137,7 @@ void ctcb_brnn_destroy(ctcb_brnn *h);
  * probs_out : optional [Tmax][B][outputDim] softmax output (forward-only mode when grads==NULL,
  *             brnnet.py:171-173)
  * stats_out : optional device float[4] = {number of non-skipped utterances, sum of their nll,
- *             number skipped, 0}.  Callers place it directly behind the flat gradient so that the
+ *             number skipped, sweep error flag (see ctcb_brnn_error_flag_offset)}.  Callers place it directly behind the flat gradient so that the
  *             data-parallel all-reduce of the gradient carries it along.
  */
 int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_per_utt,
@@ -142,6 +145,13 @@ int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_p
                             const float *params, float *grads, float *cost_out, int32_t *skip_out,
                             float *regcost_out, float *probs_out, float *stats_out,
                             void *workspace, size_t ws_bytes, void *stream);
+
+/* L2 regularisation under data parallelism.  By default ctcb_brnn_cost_and_grad adds reg*W to the weight
+ * gradients itself (brnnet.py:197-198,244-247).  A data-parallel caller SUMS the gradient over ranks and must
+ * add reg*W exactly once: it switches the handle to deferred mode (the call then only reports the L2 cost) and
+ * calls ctcb_brnn_apply_l2_f32 on the reduced gradient. */
+int ctcb_brnn_set_deferred_l2(ctcb_brnn *h, int deferred);
+int ctcb_brnn_apply_l2_f32(ctcb_brnn *h, const float *params, float *grads, void *stream);
 
 /* ---- the time recurrences of the temporal layer on their own (replaces the per-frame loops
  *      brnnet.py:144-152 [mode 0] and brnnet.py:208-224 [mode 1]) -------------------------------
@@ -168,6 +178,28 @@ int ctcb_sumsq_f32(const float *g, int64_t n, float *gnorm2_out, void *scratch, 
  * reference's `if skip: continue` does (sgd.py:109-111). */
 int ctcb_sgd_nesterov_step_f32(float *w, float *v, const float *g, int64_t n, float mom, float alpha,
                                float max_gnorm, const float *gnorm2, const float *n_valid, void *stream);
+
+/* ---- data-parallel exchange (the reference's only device hook is CUDA_DEVICE,
+ *      ctc_fast/runNNet.py:117-120, and it has no multi-GPU path) -------------------------------------
+ * One process per GPU.  Rank 0 obtains an id (HOST buffer of CTCB_COMM_ID_BYTES) and hands it to the other ranks by
+ * whatever channel the host program has (a file, MPI, torch.distributed ...); every rank then creates its
+ * communicator with the device it computes on current.  NCCL is loaded at run time (libnccl.so.2). */
+#define CTCB_COMM_ID_BYTES 128
+typedef struct ctcb_comm ctcb_comm;
+int ctcb_comm_get_unique_id(void *id_out /* HOST */);
+int ctcb_comm_create(const void *id /* HOST */, int rank, int world, ctcb_comm **out);
+void ctcb_comm_destroy(ctcb_comm *comm);
+int ctcb_comm_rank(const ctcb_comm *comm);
+int ctcb_comm_world(const ctcb_comm *comm);
+/* grads[0..n) <- sum over ranks, in place, asynchronous on `stream` (one ncclAllReduce over NVLink). */
+int ctcb_allreduce_grads(ctcb_comm *comm, float *grads, int64_t n, void *stream);
+/* Attach a communicator to a net: ctcb_brnn_cost_and_grad then performs the exchange itself -- the gradients of the
+ * layers at and above the temporal layer are summed over ranks on an internal side stream WHILE the BPTT sweep runs,
+ * the remaining tensors and the statistics tail (stats_out, normally grads + param_count) in one grouped launch at
+ * the end -- and adds the L2 term once, after the sum.  On return (stream order) `grads` holds the global gradient. */
+int ctcb_brnn_set_comm(ctcb_brnn *h, ctcb_comm *comm);
+/* For a rank whose shard of the step is empty: the same sequence of collectives on a zero-filled gradient. */
+int ctcb_brnn_exchange_only(ctcb_brnn *h, const float *params, float *grads, float *stats_out, void *stream);
 
 #ifdef __cplusplus
 }

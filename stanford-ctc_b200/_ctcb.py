@@ -56,6 +56,16 @@ _PROTOS = {
                                         c_vp, c_vp, c_vp, c_sz, c_vp]),
     "ctcb_brnn_sweep_f32": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32,
                                     c_vp, c_vp]),
+    "ctcb_brnn_set_deferred_l2": (c_int, [c_vp, c_int]),
+    "ctcb_brnn_apply_l2_f32": (c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "ctcb_comm_get_unique_id": (c_int, [c_vp]),
+    "ctcb_comm_create": (c_int, [c_vp, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "ctcb_comm_destroy": (None, [c_vp]),
+    "ctcb_comm_rank": (c_int, [c_vp]),
+    "ctcb_comm_world": (c_int, [c_vp]),
+    "ctcb_allreduce_grads": (c_int, [c_vp, c_vp, c_i64, c_vp]),
+    "ctcb_brnn_set_comm": (c_int, [c_vp, c_vp]),
+    "ctcb_brnn_exchange_only": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
     "ctcb_axpy_f32": (c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),
     "ctcb_sumsq_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ctcb_sgd_nesterov_step_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp]),

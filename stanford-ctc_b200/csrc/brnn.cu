@@ -24,6 +24,8 @@ int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *p
               unsigned int *counters, cudaStream_t st);
 int run_add2(const float *x, const float *y, float *z, int64_t n, cudaStream_t st);
 int run_sumsq(const float *g, int64_t n, float *out, float scale, int accumulate, void *scratch, cudaStream_t st);
+int comm_allreduce_ranges(ctcb_comm *c, float *const *ptrs, const int64_t *counts, int k, cudaStream_t st);
+int comm_world(const ctcb_comm *c);
 
 // ---- small kernels ---------------------------------------------------------------------------
 // column sums of a row-major R x N matrix: stage 1 partials over row blocks, stage 2 final
@@ -71,15 +73,17 @@ __global__ void softmax_rows_kernel(const float *__restrict__ x, float *__restri
 
 __global__ void set_scalar_kernel(float *p, float v) { *p = v; }
 
-// stats = {#non-skipped, sum of their nll, #skipped, 0}; one warp
-__global__ void batch_stats_kernel(const float *__restrict__ cost, const int32_t *__restrict__ skip, int B, float *stats) {
+// stats = {#non-skipped, sum of their nll, #skipped, sweep error flag}; one warp.  The flag rides in the data-parallel
+// all-reduce with the rest of the tail, so a wait timeout on one rank is seen (non-zero) by every rank.
+__global__ void batch_stats_kernel(const float *__restrict__ cost, const int32_t *__restrict__ skip, int B, float *stats,
+                                   const unsigned int *__restrict__ errflag) {
     float nv = 0.f, cs = 0.f, ns = 0.f;
     for (int u = threadIdx.x; u < B; u += 32) {
         if (skip[u]) ns += 1.f;
         else { nv += 1.f; cs += cost[u]; }
     }
     nv = warp_sum(nv); cs = warp_sum(cs); ns = warp_sum(ns);
-    if (threadIdx.x == 0) { stats[0] = nv; stats[1] = cs; stats[2] = ns; stats[3] = 0.f; }
+    if (threadIdx.x == 0) { stats[0] = nv; stats[1] = cs; stats[2] = ns; stats[3] = (float)errflag[0]; }
 }
 
 }  // namespace ctcb
@@ -97,6 +101,12 @@ struct ctcb_brnn {
     cudaEvent_t ev_delta[66];
     cudaEvent_t ev_side;
     bool side_ready;
+    // data-parallel callers sum the gradient over ranks first and add reg*W ONCE afterwards (ctcb_brnn_apply_l2_f32);
+    // the L2 cost is still reported by every call
+    bool defer_l2;
+    // data-parallel exchange inside the step (ctcb_brnn_set_comm): the gradients of the layers at and above the temporal
+    // layer are summed over ranks on the side stream WHILE the BPTT sweep runs, the rest (+ statistics tail) at the end
+    ctcb_comm *comm;
 };
 
 static int valid_cfg(const ctcb_brnn_config *c) {
@@ -104,6 +114,7 @@ static int valid_cfg(const ctcb_brnn_config *c) {
     if (c->inputDim <= 0 || c->outputDim <= 1 || c->layerSize <= 0) return 0;
     if (c->numLayers < 1 || c->numLayers > 64) return 0;
     if (c->maxT <= 0 || c->maxB <= 0 || c->maxLabels < 0) return 0;
+    if (c->maxLabels > CTCB_CTC_MAX_LABELS) return 0;   // the CTC kernel's register-resident trellis (ctc.cu)
     return 1;
 }
 static int eff_tl(const ctcb_brnn_config *c) {
@@ -217,6 +228,9 @@ extern "C" size_t ctcb_brnn_error_flag_offset(const ctcb_brnn_config *cfg) {
 }
 
 extern "C" int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out) {
+    if (cfg && cfg->maxLabels > CTCB_CTC_MAX_LABELS)
+        return set_error(CTCB_EINVAL, "ctcb_brnn_create: maxLabels %d exceeds the CTC kernel's limit of %d labels per utterance",
+                         cfg->maxLabels, CTCB_CTC_MAX_LABELS);
     if (!valid_cfg(cfg) || !out) return set_error(CTCB_EINVAL, "ctcb_brnn_create: bad config");
     ctcb_brnn *h = new (std::nothrow) ctcb_brnn;
     if (!h) return set_error(CTCB_ENOMEM, "ctcb_brnn_create: out of host memory");
@@ -227,6 +241,8 @@ extern "C" int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out) {
     layer_sizes(cfg, h->sizes);
     h->side = nullptr;
     h->side_ready = false;
+    h->defer_l2 = false;
+    h->comm = nullptr;
     *out = h;
     return CTCB_OK;
 }
@@ -263,8 +279,31 @@ extern "C" int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t 
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: null pointer argument");
     if (T <= 0 || B <= 0 || H <= 0 || (mode != 0 && mode != 1))
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: bad sizes");
+    CTCB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 16 * sizeof(unsigned int), (cudaStream_t)stream));   // error flag
     return run_sweep(mode, T, B, H, T_per_utt, pre, Wf, Wb, outF, outB, actF, actB, maxAct,
                      (unsigned int *)scratch, (cudaStream_t)stream);
+}
+
+// The part of the flat gradient that was NOT summed early on the side stream, plus the statistics tail, in one grouped
+// NCCL launch: with an early bucket [off(2 tl), end of layer N+1) that is everything before it and everything behind it.
+static int brnn_reduce_rest(ctcb_brnn *h, float *grads, float *stats, bool early_bucket, cudaStream_t st) {
+    const ctcb_brnn_config &c = h->cfg;
+    const int64_t P = ctcb_brnn_param_count(&c);
+    float *ptrs[3];
+    int64_t cnt[3];
+    int k = 0;
+    int64_t lo = P, hi = P;      // [lo, hi) was reduced early
+    if (early_bucket) {
+        int64_t o; int32_t r, cc;
+        ctcb_brnn_tensor_info(&c, 2 * h->tl, &lo, nullptr, nullptr);
+        ctcb_brnn_tensor_info(&c, 2 * c.numLayers + 1, &o, &r, &cc);
+        hi = o + (int64_t)r * cc;
+    }
+    ptrs[k] = grads; cnt[k] = lo; ++k;
+    const bool tail_adjacent = (stats == grads + P);
+    ptrs[k] = grads + hi; cnt[k] = P - hi + (stats && tail_adjacent ? 4 : 0); ++k;
+    if (stats && !tail_adjacent) { ptrs[k] = stats; cnt[k] = 4; ++k; }
+    return comm_allreduce_ranges(h->comm, ptrs, cnt, k, st);
 }
 
 extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const int32_t *T_per_utt,
@@ -309,6 +348,8 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
     // activations of layer i as the next layer (and the weight gradients) see them: the uni-directional temporal
     // layer's output IS the forward sweep (rnnet.py:112-116), the bi-directional one's is For + Back
     auto Act = [&](int i) -> float * { return (uni && i == tl && tl > 0) ? For : Xbuf(i); };
+    // the sweep kernels' error flag (word 0) is cleared once per call, so a forward-sweep timeout survives the BPTT sweep
+    CTCB_CUDA_CHECK(cudaMemsetAsync(counters, 0, 16 * sizeof(unsigned int), st));
 
     // ---------------------------------------------------------------- forward (brnnet.py:136-157)
     for (int i = 1; i <= N + 1; ++i) {
@@ -347,13 +388,9 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
                                c.maxLabels, 0, dbuf(N + 1), cost_out, skip_out, ws + w.ctc, w.gemm - w.ctc, st));
     }
 
-    if (stats_out) {
-        batch_stats_kernel<<<1, 32, 0, st>>>(cost_out, skip_out, B, stats_out);
-        CTCB_LAUNCH_CHECK();
-    }
-
     // ---------------------------------------------------------------- backward (brnnet.py:188-243)
     const bool overlap = (tl > 0);     // layers i >= tl: dW/db on the side stream, delta chain + BPTT on the main one
+    const bool dp = (h->comm != nullptr) && comm_world(h->comm) > 1;
     if (overlap) TRY(ensure_side_stream(h));
     void *gws2 = ws + w.gemm2;
     const size_t gws2_bytes = w.colsum - w.gemm2;
@@ -382,6 +419,13 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
             CTCB_LAUNCH_CHECK();
             colsum_stage2<<<(n_out + 127) / 128, 128, 0, sw>>>(part, nblk, n_out, G(2 * i + 1));
             CTCB_LAUNCH_CHECK();
+        }
+        if (dp && on_side && i == tl) {
+            // every gradient tensor of the layers >= tl is now queued on the side stream: sum that contiguous range over
+            // the ranks there, next to the BPTT sweep on the main stream
+            float *pa = G(2 * tl);
+            const int64_t na = (G(2 * N + 1) + sz[N + 1]) - pa;
+            TRY(comm_allreduce_ranges(h->comm, &pa, &na, 1, h->side));
         }
         if (i > 0) {
             float *doth = dbuf(i);
@@ -429,6 +473,13 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
         if (!uni) CTCB_CUDA_CHECK(cudaMemsetAsync(G(iWtb + 1), 0, sizeof(float), st));
     }
 
+    if (stats_out) {     // after both sweeps, so that the tail carries the error flag of either
+        batch_stats_kernel<<<1, 32, 0, st>>>(cost_out, skip_out, B, stats_out, counters);
+        CTCB_LAUNCH_CHECK();
+    }
+
+    if (dp) TRY(brnn_reduce_rest(h, grads, stats_out, overlap, st));
+
     // ---------------------------------------------------------------- L2 (brnnet.py:177-183,197-198,244-247)
     if (regcost_out) {
         set_scalar_kernel<<<1, 1, 0, st>>>(regcost_out, 0.f);
@@ -440,9 +491,55 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
             int64_t off; int32_t r, cc;
             ctcb_brnn_tensor_info(&c, idx, &off, &r, &cc);
             const int64_t n = (int64_t)r * cc;
-            TRY(ctcb_axpy_f32(grads + off, params + off, c.reg, n, st));
+            if (!h->defer_l2) TRY(ctcb_axpy_f32(grads + off, params + off, c.reg, n, st));
             if (regcost_out) TRY(run_sumsq(params + off, n, regcost_out, 0.5f * c.reg, 1, ws + w.scratch, st));
         }
     }
+    return CTCB_OK;
+}
+
+extern "C" int ctcb_brnn_set_deferred_l2(ctcb_brnn *h, int deferred) {
+    if (!h) return set_error(CTCB_EINVAL, "ctcb_brnn_set_deferred_l2: null handle");
+    h->defer_l2 = (deferred != 0);
+    return CTCB_OK;
+}
+
+extern "C" int ctcb_brnn_apply_l2_f32(ctcb_brnn *h, const float *params, float *grads, void *stream) {
+    if (!h || !params || !grads) return set_error(CTCB_EINVAL, "ctcb_brnn_apply_l2_f32: null pointer argument");
+    const ctcb_brnn_config &c = h->cfg;
+    if (c.reg <= 0.f) return CTCB_OK;
+    const int nt = ctcb_brnn_num_tensors(&c);
+    for (int idx = 0; idx < nt; idx += 2) {     // weight matrices only, as brnnet.py:197-198,244-247
+        int64_t off; int32_t r, cc;
+        ctcb_brnn_tensor_info(&c, idx, &off, &r, &cc);
+        TRY(ctcb_axpy_f32(grads + off, params + off, c.reg, (int64_t)r * cc, stream));
+    }
+    return CTCB_OK;
+}
+
+extern "C" int ctcb_brnn_set_comm(ctcb_brnn *h, ctcb_comm *comm) {
+    if (!h) return set_error(CTCB_EINVAL, "ctcb_brnn_set_comm: null handle");
+    h->comm = comm;
+    return CTCB_OK;
+}
+
+// The exchange half of a data-parallel step for a rank that had NO utterance this step: `grads` (zero-filled by the
+// caller, statistics tail included) goes through the same sequence of collectives as ctcb_brnn_cost_and_grad issues.
+extern "C" int ctcb_brnn_exchange_only(ctcb_brnn *h, const float *params, float *grads, float *stats_out, void *stream) {
+    if (!h || !params || !grads) return set_error(CTCB_EINVAL, "ctcb_brnn_exchange_only: null pointer argument");
+    if (!h->comm || comm_world(h->comm) <= 1) return CTCB_OK;
+    const ctcb_brnn_config &c = h->cfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool early = (h->tl > 0);
+    if (early) {
+        int64_t lo, o; int32_t r, cc;
+        ctcb_brnn_tensor_info(&c, 2 * h->tl, &lo, nullptr, nullptr);
+        ctcb_brnn_tensor_info(&c, 2 * c.numLayers + 1, &o, &r, &cc);
+        float *pa = grads + lo;
+        const int64_t na = o + (int64_t)r * cc - lo;
+        TRY(comm_allreduce_ranges(h->comm, &pa, &na, 1, st));
+    }
+    TRY(brnn_reduce_rest(h, grads, stats_out, early, st));
+    if (c.reg > 0.f && !h->defer_l2) return ctcb_brnn_apply_l2_f32(h, params, grads, stream);
     return CTCB_OK;
 }

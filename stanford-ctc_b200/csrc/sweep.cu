@@ -213,8 +213,8 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
     if (parts > 500) parts = 500;   // counters region holds 1024 words
     if (parts < 1) parts = 1;
     a.parts = parts;
-    a.counters += 16;     // words [0..15] are reserved for error flags
-    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters - 16, 0, sizeof(unsigned int) * (16 + a.ndir * parts), st));
+    a.counters += 16;     // words [0..15] are reserved for error flags, which the CALLER clears (once per step)
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * (a.ndir * parts), st));
     dim3 grid(slices, parts, a.ndir);
     void *params[] = {&a};
     CTCB_CUDA_CHECK(cudaLaunchCooperativeKernel((void *)sweep_kernel<KI>, grid, dim3(SW_THREADS), params, smem, st));
@@ -244,7 +244,6 @@ int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *p
         }
         if (!force_barrier) {
             bool handled = false;
-            CTCB_CUDA_CHECK(cudaMemsetAsync(counters, 0, sizeof(unsigned int) * 4, st));
             const int rc = run_sweep_cluster(mode, T, B, H, Tlen, pre, Wf, Wb, outF, outB, actF, actB, maxAct, counters, st, &handled);
             if (rc == CTCB_OK && handled) return CTCB_OK;
             if (rc != CTCB_OK) cudaGetLastError();   // cluster launch refused: fall through to the general kernel

@@ -27,6 +27,8 @@ import numpy as np
 import _ctcb
 from _ctcb import lib, check, ptr, BrnnConfig
 
+CTC_MAX_LABELS = 511      # CTCB_CTC_MAX_LABELS
+
 
 class DeviceBatch(object):
     """A minibatch staged for the device: pinned host staging buffers + device tensors.
@@ -34,6 +36,7 @@ class DeviceBatch(object):
 
     def __init__(self, torch, dev, maxT, maxB, inputDim, maxLabels):
         self.maxT, self.maxB, self.D = maxT, maxB, inputDim
+        self.maxLabels = maxLabels
         self.h_feats = torch.zeros(maxT * maxB * inputDim, dtype=torch.float32).pin_memory()
         self.h_lens = torch.zeros(maxB, dtype=torch.int32).pin_memory()
         self.h_labels = torch.zeros(max(1, maxB * maxLabels), dtype=torch.int32).pin_memory()
@@ -69,6 +72,9 @@ class DeviceBatch(object):
             n = 0
             for u, l in enumerate(labelss):
                 l = np.asarray(l, dtype=np.int32).reshape(-1)
+                if l.shape[0] > self.maxLabels:
+                    raise ValueError("utterance %d has %d labels; this net was built for at most maxLabels=%d"
+                                     % (u, l.shape[0], self.maxLabels))
                 lab[n:n + l.shape[0]] = l
                 n += l.shape[0]
                 off[u + 1] = n
@@ -113,7 +119,12 @@ class NNet:
         self.layerSizes = [layerSize] * numLayers
         self.maxBatch = maxBatch           # frames per utterance, as in the reference
         self.maxUtts = maxUtts             # utterances per step (new)
-        self.maxLabels = maxBatch if maxLabels is None else maxLabels
+        # the CTC kernel holds at most CTC_MAX_LABELS labels per utterance (include/ctcb200.h); a reference-style
+        # constructor call (no maxLabels) gets the largest capacity that exists
+        self.maxLabels = min(maxBatch, CTC_MAX_LABELS) if maxLabels is None else maxLabels
+        if self.maxLabels > CTC_MAX_LABELS:
+            raise ValueError("maxLabels=%d: the CTC kernel supports at most %d labels per utterance"
+                             % (self.maxLabels, CTC_MAX_LABELS))
         self.train = train
         self.reg = reg
         self.regcost = 0.0
@@ -176,11 +187,14 @@ class NNet:
             w.copy_(torch.from_numpy(hw.astype(np.float32)))
             b.copy_(torch.from_numpy(hb.astype(np.float32)))
         if self.train:
-            # flat gradient + a 4-float tail {n_valid, sum nll, n_skipped, 0} that rides along in the
-            # data-parallel all-reduce (see include/ctcb200.h: stats_out)
-            self.grads_ext = torch.zeros(self.nparams + 4, dtype=torch.float32, device=self.dev)
+            # flat gradient + a 4-float tail {n_valid, sum nll, n_skipped, sweep error flag} that rides along in the
+            # data-parallel all-reduce (see include/ctcb200.h: stats_out), + 4 local floats {gnorm^2, regcost, -, -}:
+            # the 8 floats behind the gradient are the step's log record, read back with ONE 32-byte copy
+            self.grads_ext = torch.zeros(self.nparams + 8, dtype=torch.float32, device=self.dev)
             self.grads = self.grads_ext[:self.nparams]
-            self.stats = self.grads_ext[self.nparams:]
+            self.stats = self.grads_ext[self.nparams:self.nparams + 4]
+            self.record = self.grads_ext[self.nparams:self.nparams + 8]
+            self._gnorm2 = self.grads_ext[self.nparams + 4:self.nparams + 5]
             self.grad = self._views(self.grads)
         else:
             self.grads = None
@@ -191,10 +205,18 @@ class NNet:
         self._errflag = self._ws[off:off + 4].view(torch.int32)      # set by the sweep kernels on a wait timeout
         self._batch = DeviceBatch(torch, self.dev, self.maxBatch, self.maxUtts, self.inputDim, self.maxLabels)
         self._batch_alt = None      # second staging buffer, created on first use by SGD.run's prefetch
-        self._cost = torch.zeros(self.maxUtts, dtype=torch.float32, device=self.dev)
-        self._skip = torch.zeros(self.maxUtts, dtype=torch.int32, device=self.dev)
-        self._regcost = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        # per-utterance outputs: cost (float32) and skip (int32) share one buffer -> one D2H copy reads both
+        self._out = torch.zeros(2 * self.maxUtts, dtype=torch.float32, device=self.dev)
+        self._cost = self._out[:self.maxUtts]
+        self._skip = self._out[self.maxUtts:].view(torch.int32)
+        if self.train:
+            self._regcost = self.grads_ext[self.nparams + 5:self.nparams + 6]
+        else:
+            self._regcost = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._out_host = torch.zeros(2 * self.maxUtts, dtype=torch.float32).pin_memory()
+        self._rec_host = torch.zeros(8, dtype=torch.float32).pin_memory()
         self._probs = None
+        self._comm = None
 
     def swap_batches(self):
         """Double buffering of the staging area: returns the buffer that is NOT the current one and makes it
@@ -240,14 +262,20 @@ class NNet:
         """Minibatch costAndGrad from host arrays: gradients of the utterances are summed.
         Returns (costs float64[B], self.grad, skips bool[B]); the L2 term is in self.regcost."""
         self._batch.pack(datas, labelss).upload()
-        cost, skip = self.costAndGradDevice(self._batch)
-        host = self._torch.cat([cost, skip.to(self._torch.float32), self._regcost,
-                                self._errflag.to(self._torch.float32)]).cpu().numpy()
+        self.costAndGradDevice(self._batch)
+        # two pinned D2H copies on the stream (no kernels, no allocation), one synchronisation
+        self._out_host.copy_(self._out, non_blocking=True)
+        self._rec_host.copy_(self.record, non_blocking=True)
+        self._torch.cuda.current_stream().synchronize()
         B = len(datas)
-        if host[2 * B + 1] != 0:
-            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[2 * B + 1]))
-        self.regcost = float(host[2 * B])
-        return host[:B].astype(np.float64), self.grad, host[B:2 * B] != 0
+        rec = self._rec_host.numpy()
+        if rec[3] != 0:
+            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(rec[3]))
+        self.regcost = float(rec[5])
+        out = self._out_host.numpy()
+        costs = out[:B].astype(np.float64)
+        skips = out[self.maxUtts:self.maxUtts + B].view(np.int32) != 0
+        return costs, self.grad, skips
 
     def costAndGrad(self, data, labels=None, sentence=None):
         """Reference signature (brnnet.py:117): data is inputDim x T float32; returns (cost, grad, skip)
@@ -257,7 +285,11 @@ class NNet:
         if not self.train:
             self._batch.pack([data], None).upload()
             probs = self.costAndGradDevice(self._batch)
-            return np.ascontiguousarray(probs.view(T, self.outputDim).cpu().numpy().T)
+            out = np.ascontiguousarray(probs.view(T, self.outputDim).cpu().numpy().T)
+            flag = int(self._errflag.item())
+            if flag != 0:
+                raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % flag)
+            return out
         costs, grad, skips = self.costAndGradBatch([data], [labels])
         cost = float(costs[0])
         if self.reg > 0:

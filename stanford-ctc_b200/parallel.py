@@ -15,7 +15,7 @@ def shard(items, rank, world):
     return list(items[rank::world])
 
 
-def select_step_utterances(data_dict, alis, chunk, max_frames, rank, world, log=None):
+def select_step_utterances(data_dict, alis, chunk, max_frames, rank, world, log=None, max_labels=None):
     """The utterances of one step that THIS rank computes.  The reference's per-utterance admission rules
     (sgd.py:76-88: skip when longer than the buffers, skip when there are fewer frames than labels) are applied
     to the whole step in the same order on every rank -- two cheap length look-ups per key -- and only then is
@@ -31,6 +31,11 @@ def select_step_utterances(data_dict, alis, chunk, max_frames, rank, world, log=
         if nframes < nlab:
             if log:
                 log("SKIPPING utt frames less than label length (Utterance length %d, Num Labels %d)." % (nframes, nlab))
+            continue
+        if max_labels is not None and nlab > max_labels:
+            # not a reference rule: the device buffers (and the CTC kernel) hold at most max_labels labels per utterance
+            if log:
+                log("SKIPPING utt label sequence exceeds the label capacity (Num Labels %d, capacity %d)." % (nlab, max_labels))
             continue
         used.append(k)
     return shard(used, rank, world)

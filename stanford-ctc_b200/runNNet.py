@@ -124,7 +124,14 @@ def run(args=None):
     if resumed:
         out_dir = cfg["output_dir"]
     else:
+        # the run directory is named by rank 0's clock and SHARED: ranks started a second apart would otherwise
+        # log into (and resume from) directories that do not exist
         out_dir = os.path.join(cli.runDir, str(TimeString()))
+        if world > 1:
+            import torch.distributed as dist
+            box = [out_dir]
+            dist.broadcast_object_list(box, src=0)
+            out_dir = box[0]
         if rank == 0:
             os.makedirs(out_dir, exist_ok=True)
         cli.cfg_file = os.path.join(out_dir, "cfg.json")

@@ -44,11 +44,12 @@ class SGD:
 
         self._vflat = torch.zeros(model.nparams, dtype=torch.float32, device=model.dev)
         self.velocity = FlatList(model._views(self._vflat), self._vflat)
-        self._gnorm2 = torch.zeros(1, dtype=torch.float32, device=model.dev)
+        self._gnorm2 = model._gnorm2          # lives in the 8-float record behind the flat gradient
         self._scratch = torch.zeros(8192, dtype=torch.uint8, device=model.dev)
-        # per-step log record {n_valid, sum nll, n_skipped, 0, gnorm^2, regcost, sweep error flag}: copied to pinned
-        # host memory on the stream right behind the step, read one step later (two slots alternate)
-        self._log_host = [torch.zeros(7, dtype=torch.float32).pin_memory() for _ in range(2)]
+        # per-step log record {n_valid, sum nll, n_skipped, sweep error flag, gnorm^2, regcost, -, -}: the 8 floats behind
+        # the flat gradient, copied to pinned host memory on the stream right behind the step (one 32-byte D2H copy,
+        # no kernel) and read one step later (two slots alternate)
+        self._log_host = [torch.zeros(8, dtype=torch.float32).pin_memory() for _ in range(2)]
         self._log_event = [torch.cuda.Event() for _ in range(2)]
         self._log_slot = 0
 
@@ -88,16 +89,33 @@ class SGD:
         stream = _ctcb.current_stream()
         # w = w + mom*velocity (evaluate gradient at future point)      sgd.py:91-93
         check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, stream))
+        # forward, CTC, backward -- and, with a communicator attached (ensure_comm), the exchange: the flat gradient and
+        # its statistics tail summed over ranks by libctcb200 itself (NCCL), part of it under the BPTT sweep
         m.costAndGradDevice(batch)
-        dist, rank, world = self._world()
-        if world > 1:
-            parallel.allreduce_sum(dist, m.grads_ext)                  # sum over ranks, NCCL
         # gnorm over all parameters as one vector                       sgd.py:103-107
         check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch), stream))
         # undo look-ahead, clip, velocity, update                       sgd.py:97-100,130-140,161
         check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams, float(mom),
                                              float(self.alpha), float(self.maxGNorm), ptr(self._gnorm2),
                                              ptr(m.stats), stream))
+
+    def ensure_comm(self):
+        """Data parallelism: create this process's ctcb communicator (once per model) and attach it to the net.  The
+        NCCL id travels over torch.distributed, which is used for nothing else on the training path."""
+        import ctypes
+        dist, rank, world = self._world()
+        m = self.model
+        if world <= 1 or m._comm is not None:
+            return
+        idbuf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            check(lib.ctcb_comm_get_unique_id(idbuf))
+        box = [idbuf.raw]
+        dist.broadcast_object_list(box, src=0)
+        comm = ctypes.c_void_p()
+        check(lib.ctcb_comm_create(box[0], rank, world, ctypes.byref(comm)))
+        check(lib.ctcb_brnn_set_comm(m._h, comm))
+        m._comm = comm
 
     def _momentum_now(self):
         return 0.5 if self.it <= 10 else self.momentum                  # sgd.py:64-74
@@ -106,7 +124,8 @@ class SGD:
         """Host side of one step: the reference's length checks (sgd.py:76-88), sharding over ranks, packing into
         the idle staging buffer and the asynchronous H2D copy."""
         m = self.model
-        used = parallel.select_step_utterances(data_dict, alis, chunk, self.maxBatch, rank, world, log=logging.info)
+        used = parallel.select_step_utterances(data_dict, alis, chunk, self.maxBatch, rank, world, log=logging.info,
+                                               max_labels=m.maxLabels)
         datas = [data_dict[k] for k in used]
         labels = [np.array(alis[k], dtype=np.int32) for k in used]     # only this rank's utterances are converted
         batch = None
@@ -124,10 +143,10 @@ class SGD:
         mom = self._momentum_now()
         if prep["batch"] is not None:
             self.step_device(prep["batch"], mom)
-        else:                  # this rank has no utterance this step: contribute zeros to the all-reduce
+        else:                  # this rank has no utterance this step: contribute zeros to the exchange
             st = _ctcb.current_stream()
             m.grads_ext.zero_()
-            parallel.allreduce_sum(dist, m.grads_ext)
+            check(lib.ctcb_brnn_exchange_only(m._h, ptr(m.params), ptr(m.grads), ptr(m.stats), st))
             check(lib.ctcb_sumsq_f32(ptr(m.grads), m.nparams, ptr(self._gnorm2), ptr(self._scratch), st))
             check(lib.ctcb_axpy_f32(ptr(m.params), ptr(self._vflat), float(mom), m.nparams, st))
             check(lib.ctcb_sgd_nesterov_step_f32(ptr(m.params), ptr(self._vflat), ptr(m.grads), m.nparams, float(mom),
@@ -135,8 +154,7 @@ class SGD:
                                                  ptr(m.stats), st))
         slot = self._log_slot
         self._log_slot ^= 1
-        rec = torch.cat([m.stats, self._gnorm2, m._regcost, m._errflag.to(torch.float32)])
-        self._log_host[slot].copy_(rec, non_blocking=True)
+        self._log_host[slot].copy_(m.record, non_blocking=True)
         self._log_event[slot].record()
         prep["slot"] = slot
 
@@ -145,8 +163,8 @@ class SGD:
         m = self.model
         self._log_event[prep["slot"]].synchronize()
         host = self._log_host[prep["slot"]].numpy().copy()
-        if host[6] != 0:
-            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[6]))
+        if host[3] != 0:       # summed over ranks with the rest of the tail: every rank raises together
+            raise RuntimeError("recurrent sweep: inter-CTA wait timed out (flag %d); results are invalid" % int(host[3]))
         nvalid, costsum = float(host[0]), float(host[1])
         gnorm = float(np.sqrt(host[4]))
         m.regcost = float(host[5])
@@ -177,6 +195,7 @@ class SGD:
         Steps are software-pipelined: while the device works on minibatch i the host checks, packs, uploads and
         enqueues minibatch i+1 (second staging buffer); step i's log record is read after that."""
         dist, rank, world = self._world()
+        self.ensure_comm()
 
         # randomly select minibatch
         random.shuffle(keys)

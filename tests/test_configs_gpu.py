@@ -1,0 +1,123 @@
+"""GPU parity at the BASELINE.json configurations themselves (the shapes bench.py times), full network through
+nnets.brnnet.NNet.costAndGradBatch against the float64 oracle (oracle/brnn_oracle.py, pinned to the reference's
+rnnetcpu.py) on the same seeded inputs:
+
+  C2 exactly as benchmarked   numLayers=2, temporalLayer=1, H=512,  B=32, T=200,  D=41, K=62, |l|=30
+  C3 at B=8                   numLayers=3, temporalLayer=2, H=1024,       T=800,  D=41, K=32, |l|=100
+  C4 at B=2                   numLayers=5, temporalLayer=3, H=2048,       T=1500, D=41, K=35, |l|=150
+                              (reference defaults runNNet.py:34-38, swbd-utils/runSwbd.sh:6-22)
+
+Tolerances (north_star: 1e-4 relative on loss and gradient): per-utterance cost 1e-4 relative; every gradient tensor
+||g - g_ref||_F / ||g_ref||_F <= 1e-4.  The measured errors are written to gpurun_out/parity_configs.json."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import recipes
+from oracle import brnn_oracle
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+COST_TOL, GRAD_TOL = 1e-4, 1e-4
+
+CASES = {
+    "c2_as_benchmarked": dict(D=41, K=62, H=512, N=2, tl=1, T=200, L=30, B=32),
+    "c3_b8": dict(D=41, K=32, H=1024, N=3, tl=2, T=800, L=100, B=8),
+    "c4_b2": dict(D=41, K=35, H=2048, N=5, tl=3, T=1500, L=150, B=2),
+    # a ragged C3-shaped minibatch that is wider than one 16-utterance MMA tile of the tensor-core sweep
+    "c3_ragged_b24": dict(D=41, K=32, H=1024, N=3, tl=2, T=160, L=20, B=24, ragged=True),
+}
+
+
+def _rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def _record(name, rec):
+    out = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    p = os.path.join(out, "parity_configs.json")
+    d = json.load(open(p)) if os.path.exists(p) else {}
+    d[name] = rec
+    json.dump(d, open(p, "w"), indent=1)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_full_net_at_baseline_config(name, cuda):
+    import nnets.brnnet as rnnet
+    c = CASES[name]
+    D, K, H, N, tl, T, L, B = (c[k] for k in ("D", "K", "H", "N", "tl", "T", "L", "B"))
+    rng = np.random.RandomState(5)
+    if c.get("ragged"):
+        lens = [int(x) for x in rng.randint(int(0.6 * T), T + 1, size=B)]
+        lens[0] = T
+        nlabs = [int(x) for x in rng.randint(3, L + 1, size=B)]
+    else:
+        lens, nlabs = [T] * B, [L] * B
+    datas, labelss = recipes.synth_batch(D, K, lens, nlabs, seed=33)
+    np.random.seed(33)
+    on = brnn_oracle.NNet(D, K, H, N, T, temporalLayer=tl, dtype=np.float64)
+    on.initParams()
+    np.random.seed(33)
+    nn = rnnet.NNet(D, K, H, N, T, temporalLayer=tl, maxUtts=B, maxLabels=L)
+    nn.initParams()
+    costs, grad, skips = nn.costAndGradBatch(datas, labelss)
+    g_host = [(dw.cpu().numpy().astype(np.float64), db.cpu().numpy().astype(np.float64)) for dw, db in grad]
+    del nn
+    cuda.cuda.empty_cache()
+    o_costs, o_grad, o_skips = on.costAndGradBatch(datas, labelss)
+    assert np.array_equal(skips, o_skips) and not skips.any()
+    cost_err = float(np.max(np.abs(costs - o_costs) / np.abs(o_costs)))
+    errs = []
+    for i, ((dw, db), (odw, odb)) in enumerate(zip(g_host, o_grad)):
+        errs.append(_rel(dw, odw))
+        if i <= N:
+            errs.append(_rel(db.reshape(-1), odb.reshape(-1)))
+    _record(name, dict(config=c, cost_rel_err_max=cost_err, grad_rel_err_max=max(errs), grad_rel_err_per_tensor=errs,
+                       tolerance=dict(cost=COST_TOL, grad=GRAD_TOL)))
+    assert cost_err <= COST_TOL, cost_err
+    assert max(errs) <= GRAD_TOL, errs
+
+
+def test_two_shards_summed_equal_the_full_batch_with_l2(cuda):
+    """The data-parallel arithmetic without NCCL, on one GPU: two nets with the same parameters each compute one rank's
+    round-robin shard with the L2 term deferred (ctcb_brnn_set_deferred_l2), the gradients and statistics tails are
+    added, reg*W is applied ONCE (ctcb_brnn_apply_l2_f32), and the result must equal the single-GPU gradient of the
+    full minibatch with reg > 0 (a per-rank L2 term would count world times)."""
+    import _ctcb
+    from _ctcb import lib, check, ptr
+    import nnets.brnnet as rnnet
+    import parallel
+    D, K, H, N, tl, reg = 13, 11, 64, 3, 2, 1e-2
+    lens, nlabs = [37, 50, 21, 50, 8, 44, 29], [9, 14, 5, 20, 3, 11, 7]
+    datas, labelss = recipes.synth_batch(D, K, lens, nlabs, seed=7)
+
+    def net(maxUtts):
+        np.random.seed(4)
+        nn = rnnet.NNet(D, K, H, N, 50, temporalLayer=tl, reg=reg, maxUtts=maxUtts, maxLabels=20)
+        nn.initParams()
+        return nn
+
+    full = net(7)
+    costs, _, _ = full.costAndGradBatch(datas, labelss)
+    g_full = full.grads_ext[:full.nparams + 4].clone()
+    st = _ctcb.current_stream()
+    total = None
+    for rank in range(2):
+        idx = parallel.shard(list(range(7)), rank, 2)
+        nn = net(4)
+        check(lib.ctcb_brnn_set_deferred_l2(nn._h, 1))
+        nn.costAndGradBatch([datas[i] for i in idx], [labelss[i] for i in idx])
+        part = nn.grads_ext[:nn.nparams + 4].clone()
+        total = part if total is None else total + part        # what the all-reduce computes
+        last = nn
+    check(lib.ctcb_brnn_apply_l2_f32(last._h, ptr(last.params), ptr(total), st))
+    cuda.cuda.synchronize()
+    a, b = total.cpu().numpy().astype(np.float64), g_full.cpu().numpy().astype(np.float64)
+    assert _rel(a[:-4], b[:-4]) < 2e-6
+    assert a[-4] == b[-4] == 7 and abs(a[-3] - b[-3]) / abs(b[-3]) < 1e-6 and a[-2] == b[-2] == 0 and a[-1] == b[-1] == 0
+    # and the naive per-rank L2 would NOT have matched: the deferred sum differs from it by exactly reg*W
+    w = full.params.cpu().numpy().astype(np.float64)
+    assert np.linalg.norm(reg * w) > 1e-3 * np.linalg.norm(b[:-4])

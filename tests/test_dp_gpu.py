@@ -1,5 +1,6 @@
-"""GPU data-parallel test (needs >= 2 GPUs; skipped otherwise): two ranks over NCCL, each with its shard of
-the step's utterances, must end with bit-identical parameters that match the single-GPU step on the full
+"""GPU data-parallel test (needs >= 2 GPUs; skipped otherwise; the same arithmetic without NCCL is covered on one GPU by
+tests/test_configs_gpu.py::test_two_shards_summed_equal_the_full_batch_with_l2): two ranks over NCCL (reg > 0, so the L2
+term must be added once, after the sum), each with its shard of the step's utterances, must end with bit-identical parameters that match the single-GPU step on the full
 minibatch (the all-reduce sums the flat gradient + statistics tail; sgd.py:91-161 semantics)."""
 import os
 import subprocess
@@ -25,7 +26,7 @@ datas, labelss = recipes.synth_batch(13, 11, [25, 30, 18, 30, 22, 27], [6, 8, 4,
 keys = ["k%%d" %% i for i in range(6)]
 dd = dict(zip(keys, datas)); alis = dict(zip(keys, [list(map(str, l)) for l in labelss]))
 np.random.seed(2); random.seed(33)
-nn = rnnet.NNet(13, 11, 64, 2, 30, temporalLayer=1, maxUtts=parallel.per_rank_capacity(6, world), maxLabels=10)
+nn = rnnet.NNet(13, 11, 64, 2, 30, temporalLayer=1, reg=1e-3, maxUtts=parallel.per_rank_capacity(6, world), maxLabels=10)
 nn.initParams()
 opt = sgd.SGD(nn, 30, alpha=1e-3, momentum=0.9, maxGradNorm=5.0, batchSize=6, verbose=False)
 for _ in range(3):
