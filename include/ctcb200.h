@@ -160,10 +160,15 @@ int ctcb_brnn_apply_l2_f32(ctcb_brnn *h, const float *params, float *grads, void
  * mode 1: outF[t] = within(actF[t]) * (pre[t] + outF[t+1].Wf), outB mirrored.
  * Wb == NULL (with outB/actB ignored) runs the forward-in-time direction alone: the uni-directional layer of
  * nnets/rnnet.py:112-116 [mode 0] and :162-177 [mode 1].
- * scratch: >= 4096 bytes of device memory (error flag + diagnostics). */
+ * scratch: device memory, >= 4096 bytes (word 0 = error flag, cleared by the call); with
+ * ctcb_brnn_sweep_workspace_bytes(H) bytes the tensor-core kernel (H >= 1024, sweep_tc.cu) can also run mode 1, which
+ * needs room for the transposed recurrent matrices. */
+size_t ctcb_brnn_sweep_workspace_bytes(int H);
 int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
                         const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
-                        const float *actB, float maxAct, void *scratch, void *stream);
+                        const float *actB, float maxAct, void *scratch, size_t scratch_bytes, void *stream);
+/* 1 when the recurrences of a (layerSize H, B utterances, bi-directional) step run on the tensor-core kernel. */
+int ctcb_sweep_uses_tensor_cores(int H, int B);
 
 /* ---- optimiser (replaces sgd.SGD.run arithmetic, ctc_fast/sgd.py:91-161, and
  *      NNet.updateParams, brnnet.py:251-256) --------------------------------------------------- */

@@ -21,7 +21,8 @@
 namespace ctcb {
 int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
               const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
-              unsigned int *counters, cudaStream_t st);
+              unsigned int *counters, void *ws, size_t ws_bytes, cudaStream_t st);
+size_t sweep_tc_workspace_bytes(int H);
 int run_add2(const float *x, const float *y, float *z, int64_t n, cudaStream_t st);
 int run_sumsq(const float *g, int64_t n, float *out, float scale, int accumulate, void *scratch, cudaStream_t st);
 int comm_allreduce_ranges(ctcb_comm *c, float *const *ptrs, const int64_t *counts, int k, cudaStream_t st);
@@ -175,7 +176,7 @@ struct WsLayout {
     size_t For, Back, dFor, dBack;
     size_t D[67];       // D[j]: gradient w.r.t. the output of affine map j (1..N+1)
     size_t gemm2, colsum2;
-    size_t ctc, gemm, colsum, scratch, counters, lens_dummy;
+    size_t ctc, gemm, colsum, scratch, counters, sweep, sweep_bytes, lens_dummy;
     size_t total;
 };
 
@@ -212,6 +213,8 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
     w.colsum2 = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
     w.scratch = take(8192);
     w.counters = take(sizeof(unsigned int) * 1024);
+    w.sweep_bytes = eff_tl(c) ? sweep_tc_workspace_bytes(H) : 0;
+    w.sweep = take(w.sweep_bytes);
     w.total = off;
     return w;
 }
@@ -273,15 +276,16 @@ static int ensure_side_stream(ctcb_brnn *h) {
 
 extern "C" int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
                                    const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
-                                   const float *actB, float maxAct, void *scratch, void *stream) {
+                                   const float *actB, float maxAct, void *scratch, size_t scratch_bytes, void *stream) {
     if (!T_per_utt || !pre || !Wf || !outF || !scratch || (mode == 1 && !actF) ||
         (Wb && (!outB || (mode == 1 && !actB))))
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: null pointer argument");
     if (T <= 0 || B <= 0 || H <= 0 || (mode != 0 && mode != 1))
         return set_error(CTCB_EINVAL, "ctcb_brnn_sweep_f32: bad sizes");
     CTCB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 16 * sizeof(unsigned int), (cudaStream_t)stream));   // error flag
+    if (scratch_bytes < 4096) return set_error(CTCB_ENOMEM, "ctcb_brnn_sweep_f32: scratch %zu < 4096 bytes", scratch_bytes);
     return run_sweep(mode, T, B, H, T_per_utt, pre, Wf, Wb, outF, outB, actF, actB, maxAct,
-                     (unsigned int *)scratch, (cudaStream_t)stream);
+                     (unsigned int *)scratch, (char *)scratch + 4096, scratch_bytes - 4096, (cudaStream_t)stream);
 }
 
 // The part of the flat gradient that was NOT summed early on the side stream, plus the statistics tail, in one grouped
@@ -364,7 +368,7 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
             {
             ProfScope ps("sweep_fwd", st);
             TRY(run_sweep(0, Tmax, B, H, T_per_utt, Xbuf(i), P(iWtf), uni ? nullptr : P(iWtb), For, Back, nullptr,
-                          nullptr, c.maxAct, counters, st));
+                          nullptr, c.maxAct, counters, ws + w.sweep, w.sweep_bytes, st));
             }
             if (!uni) {
                 ProfScope ps("elementwise", st);
@@ -440,7 +444,7 @@ extern "C" int ctcb_brnn_cost_and_grad(ctcb_brnn *h, const float *feats, const i
                 {
                 ProfScope ps("sweep_bptt", st);
                 TRY(run_sweep(1, Tmax, B, H, T_per_utt, doth, P(iWtf), uni ? nullptr : P(iWtb), dFor, dBack, For, Back,
-                              c.maxAct, counters, st));
+                              c.maxAct, counters, ws + w.sweep, w.sweep_bytes, st));
                 }
                 // recurrent weight gradients (brnnet.py:227-230): independent of the rest of the backward pass,
                 // so they go to the side stream as well
@@ -543,3 +547,5 @@ extern "C" int ctcb_brnn_exchange_only(ctcb_brnn *h, const float *params, float 
     if (c.reg > 0.f && !h->defer_l2) return ctcb_brnn_apply_l2_f32(h, params, grads, stream);
     return CTCB_OK;
 }
+
+extern "C" size_t ctcb_brnn_sweep_workspace_bytes(int H) { return 4096 + ctcb::sweep_tc_workspace_bytes(H); }

@@ -225,11 +225,21 @@ static int launch_sweep(SweepArgs &a, int slices, size_t smem, cudaStream_t st) 
 int run_sweep_cluster(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
                       const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
                       unsigned int *err, cudaStream_t st, bool *handled);
+int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf, const float *Wb,
+                 float *outF, float *outB, const float *actF, const float *actB, float maxAct, unsigned int *counters,
+                 void *ws, size_t ws_bytes, cudaStream_t st, bool *handled);
 
-// counters: 4096 bytes of device scratch
+// counters: 4096 bytes of device scratch (word 0 = error flag, cleared by the caller); ws: optional further scratch
+// (sweep_tc_workspace_bytes(H)) that lets the tensor-core kernel run the BPTT mode as well
 int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
               const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
-              unsigned int *counters, cudaStream_t st) {
+              unsigned int *counters, void *ws, size_t ws_bytes, cudaStream_t st) {
+    {   // tensor-core path (H >= 1024)
+        bool handled = false;
+        const int rc = run_sweep_tc(mode, T, B, H, Tlen, pre, Wf, Wb, outF, outB, actF, actB, maxAct, counters, ws, ws_bytes, st, &handled);
+        if (rc != CTCB_OK) return rc;
+        if (handled) return CTCB_OK;
+    }
     SweepArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.W[0] = Wf; a.W[1] = Wb; a.out[0] = outF; a.out[1] = outB; a.act[0] = actF; a.act[1] = actB;

@@ -1,0 +1,538 @@
+// sweep_tc.cu -- the temporal-layer recurrences on the 5th-generation tensor cores (H >= 1024: C3 / C4).
+//
+// Same arithmetic as sweep.cu / sweep_cluster.cu (reference loops ctc_fast/nnets/brnnet.py:144-152 forward,
+// :208-224 BPTT): per time step and direction  S_t = f(pre_t + S_{t-1} . W^T)  over ALL utterances of the batch.
+// At H >= 1024 the recurrent matrix no longer fits the register files (sweep_cluster.cu) and the general kernel
+// (sweep.cu) re-reads it per 8-utterance tile; here a step is one fp32-faithful (3xTF32, as gemm_tc.cu) tensor-core
+// contraction  D[units x utterances] = W[units x H] . S_{t-1}[utterances x H]^T  spread over the device:
+//
+//   * work split: M tiles of 128 output units x 4 K-slices (H/4 inputs each) x NS utterance splits x 2 directions
+//     = 128 CTAs at H = 1024 (NS = 2) and H = 2048 (NS = 1); one persistent CTA per SM for the whole sweep;
+//   * the 4 K-slices of an (M tile, utterance split, direction) form a CLUSTER: each CTA accumulates its partial
+//     product in tensor memory (tcgen05.mma.kind::tf32, operands staged by TMA into a 128B-swizzled ring, low halves
+//     produced on chip by splitter warps), copies it to its own shared memory, and after one cluster barrier CTA r
+//     sums the four partials of ITS quarter of the utterances through distributed shared memory
+//     (ld.shared::cluster), adds pre_t, applies clip / mask and writes S_t -- a deterministic split-K reduction
+//     that never touches global memory;
+//   * S_t goes to HBM/L2 anyway (the layer's output); the next step's B operand is TMA-loaded from there, so the only
+//     device-wide synchronisation is ONE counter barrier per step and (direction, utterance split) -- 32 or 64 CTAs;
+//   * W is streamed from L2 every step (8.4 / 33.5 MB for both directions: resident in the 126 MB L2); at H = 2048
+//     hi + lo halves of both directions (67 MB) exceed the 33 MB of shared memory on the device, so residency is
+//     not an option there, and the stream is hidden behind the MMAs whenever the batch is large enough.
+//
+// BPTT needs W^T as the A operand: a transposed copy is made once per launch (2 H^2 floats of caller scratch).
+#include "common.cuh"
+#include <cuda.h>
+#include <stdlib.h>
+
+namespace ctcb {
+
+constexpr int STC_THREADS = 256;
+constexpr int STC_CS = 4;            // K-slices = cluster size
+constexpr int STC_BM = 128;          // output units per CTA
+constexpr int STC_BK = 32;           // floats per k-block (one 128-byte swizzle span)
+constexpr uint32_t STC_A_BYTES = STC_BM * STC_BK * 4;
+
+struct SweepTcArgs {
+    int mode, T, B, H;
+    const int32_t *Tlen;
+    const float *pre;
+    float *out[2];
+    const float *act[2];
+    float maxAct;
+    unsigned int *err;        // [0]: set to 3 when a wait timed out (results invalid, never a hang)
+    unsigned int *counters;   // [ndir * NS] step counters, zeroed before launch
+    int ndir, MT, NS, Npad;   // Npad: utterances per split, multiple of 16, <= 256
+    int nkb;                  // k-blocks per K-slice = H / 4 / 32
+    int stages;
+    uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
+    uint32_t tmem_cols;
+};
+
+// ---------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t stc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void stc_mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void stc_mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool stc_mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Bounded wait: after ~1 s (or once any thread of the CTA has given up) report through *err and stop waiting, so a
+// protocol bug or a lost peer becomes an error flag, never a hung GPU.
+__device__ __forceinline__ void stc_mbar_wait(uint32_t bar, uint32_t parity, volatile int *dead, unsigned int *err) {
+    if (stc_mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!stc_mbar_try_wait(bar, parity)) {
+        if (*dead) return;
+        if (clock64() - t0 > 2000000000LL) {
+            *dead = 1;
+            atomicExch(err, 3u);
+            return;
+        }
+    }
+}
+__device__ __forceinline__ void stc_tma_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void stc_tma_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void stc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void stc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void stc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void stc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void stc_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t stc_map_to_cta(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ float4 stc_ld_cluster_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory");
+    return v;
+}
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (8-row x 128-byte atoms 1024 bytes apart), as gemm_tc.cu
+__device__ __forceinline__ uint64_t stc_smem_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ uint32_t stc_idesc(int m, int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// grid = (4 K-slices [cluster], MT * NS, ndir); 8 warps:
+//   warp 0 lane 0 : waits for the previous step's state (counter barrier), then TMA producer;
+//   warp 1 lane 0 : MMA issuer (owns the tensor-memory allocation);
+//   warps 4..7    : splitters (lo = x - tf32(x) of every landed tile, in shared memory);
+//   all 8 warps   : tensor memory -> shared partial, cluster barrier, split-K reduction over DSMEM, epilogue.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(STC_THREADS, 1)
+sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
+                const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1, SweepTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t stc_smem[];
+    uint8_t *base = (uint8_t *)(((uintptr_t)stc_smem + 1023) & ~(uintptr_t)1023);
+    const int STAGES = a.stages;
+    const uint32_t stage_bytes = a.stage_bytes;
+    const uint32_t B_BYTES = (uint32_t)a.Npad * 128u;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)STAGES * stage_bytes);
+    uint64_t *full = bars, *ready = bars + 8, *empty = bars + 16, *done = bars + 24;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 25);
+    volatile int *dead = reinterpret_cast<volatile int *>(tmem_slot + 1);
+    float *partial = reinterpret_cast<float *>(base);                 // [Npad][128], aliases the operand ring
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int rank = blockIdx.x;                                      // K-slice = rank in cluster
+    const int mt = blockIdx.y % a.MT, ns = blockIdx.y / a.MT;
+    const int dir = blockIdx.z;
+    const int B = a.B, T = a.T, H = a.H, Npad = a.Npad, nkb = a.nkb;
+    const int m0 = mt * STC_BM;
+    const int b_lo = ns * Npad;
+    const int Nc = Npad / STC_CS;                                     // utterance columns this CTA finalises
+    const bool bptt = (a.mode == 1);
+    const bool ascending = (dir == 0) != bptt;
+    const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
+    const CUtensorMap *tmS = dir ? &tmS1 : &tmS0;
+    float *out = a.out[dir];
+    const float *act = a.act[dir];
+    unsigned int *ctr = a.counters + (dir * a.NS + ns);
+    const unsigned int domain = (unsigned int)(STC_CS * a.MT);        // CTAs that share this counter
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            stc_mbar_init(stc_smem_u32(&full[s]), 1);
+            stc_mbar_init(stc_smem_u32(&ready[s]), 4);
+            stc_mbar_init(stc_smem_u32(&empty[s]), 1);
+        }
+        stc_mbar_init(stc_smem_u32(done), 1);
+        *dead = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(stc_smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    stc_fence_before();
+    __syncthreads();
+    stc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    stc_cluster_sync();
+
+    // epilogue role: warp w takes columns c = w, w + 8, ... < Nc of this CTA's quarter; lane l owns units 4l..4l+3
+    const int j4 = m0 + 4 * lane;
+    uint32_t it = 0;              // running k-block index of the ring (all roles advance it identically)
+
+    for (int s = 0; s < T; ++s) {
+        const int t = ascending ? s : T - 1 - s;
+        const int tprev = ascending ? t - 1 : t + 1;
+        // operands of the epilogue that do not depend on the recurrence: issued before the waits
+        float4 pre_v[8], act_v[8];
+        int Tb[8];
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            const int c = warp + 8 * ci;
+            const int b = b_lo + rank * Nc + c;
+            pre_v[ci] = make_float4(0.f, 0.f, 0.f, 0.f);
+            act_v[ci] = pre_v[ci];
+            Tb[ci] = 0;
+            if (c < Nc && b < B) {
+                const int64_t o = ((int64_t)t * B + b) * H + j4;
+                pre_v[ci] = __ldg(reinterpret_cast<const float4 *>(a.pre + o));
+                if (bptt) act_v[ci] = __ldg(reinterpret_cast<const float4 *>(act + o));
+                Tb[ci] = __ldg(a.Tlen + b);
+            }
+        }
+        if (s > 0) {
+            if (warp == 0 && lane == 0) {
+                // ---------------------------------------------------- wait for S_{t-1}, then TMA producer
+                const unsigned int target = domain * (unsigned int)s;
+                unsigned int v;
+                const long long t0 = clock64();
+                do {
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                    if (v >= target || *dead) break;
+                    if (clock64() - t0 > 2000000000LL) { *dead = 1; atomicExch(a.err, 3u); break; }
+                } while (true);
+                asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
+                for (int i = 0; i < nkb; ++i) {
+                    const uint32_t g = it + (uint32_t)i;
+                    const int st = (int)(g % (uint32_t)STAGES);
+                    const uint32_t use = g / (uint32_t)STAGES;
+                    if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                    const uint32_t fb = stc_smem_u32(&full[st]);
+                    stc_mbar_expect_tx(fb, STC_A_BYTES + B_BYTES);
+                    uint8_t *sp = base + (size_t)st * stage_bytes;
+                    const int k = (rank * nkb + i) * STC_BK;
+                    stc_tma_2d(stc_smem_u32(sp), tmW, fb, k, m0);
+                    stc_tma_3d(stc_smem_u32(sp + 2 * STC_A_BYTES), tmS, fb, k, b_lo, tprev);
+                }
+            } else if (warp == 1 && lane == 0) {
+                // ---------------------------------------------------- MMA issuer
+                const uint32_t idesc = stc_idesc(STC_BM, Npad);
+                for (int i = 0; i < nkb; ++i) {
+                    const uint32_t g = it + (uint32_t)i;
+                    const int st = (int)(g % (uint32_t)STAGES);
+                    const uint32_t use = g / (uint32_t)STAGES;
+                    stc_mbar_wait(stc_smem_u32(&ready[st]), use & 1, dead, a.err);
+                    stc_fence_after();
+                    const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
+                    const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
+                    const uint64_t dB = stc_smem_desc(sa + 2 * STC_A_BYTES), dBl = stc_smem_desc(sa + 2 * STC_A_BYTES + B_BYTES);
+#pragma unroll
+                    for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
+                        const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+                        stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                        stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
+                        stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                    }
+                    stc_commit(stc_smem_u32(&empty[st]));
+                }
+                stc_commit(stc_smem_u32(done));
+            } else if (warp >= 4) {
+                // ---------------------------------------------------- splitters (128 threads)
+                const int stid = tid - 128;
+                for (int i = 0; i < nkb; ++i) {
+                    const uint32_t g = it + (uint32_t)i;
+                    const int st = (int)(g % (uint32_t)STAGES);
+                    const uint32_t use = g / (uint32_t)STAGES;
+                    stc_mbar_wait(stc_smem_u32(&full[st]), use & 1, dead, a.err);
+                    uint8_t *sp = base + (size_t)st * stage_bytes;
+                    const float4 *hiA = reinterpret_cast<const float4 *>(sp);
+                    float4 *loA = reinterpret_cast<float4 *>(sp + STC_A_BYTES);
+                    const float4 *hiB = reinterpret_cast<const float4 *>(sp + 2 * STC_A_BYTES);
+                    float4 *loB = reinterpret_cast<float4 *>(sp + 2 * STC_A_BYTES + B_BYTES);
+                    auto lo4 = [](float4 v) {
+                        float4 r;
+                        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                        return r;
+                    };
+#pragma unroll
+                    for (int q = 0; q < (int)(STC_A_BYTES / 16 / 128); ++q) loA[stid + q * 128] = lo4(hiA[stid + q * 128]);
+                    const int nb4 = (int)(B_BYTES / 16);
+                    for (int q = stid; q < nb4; q += 128) loB[q] = lo4(hiB[q]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(stc_smem_u32(&ready[st])) : "memory");
+                }
+            }
+            it += (uint32_t)nkb;
+            __syncwarp();
+            // -------------------------------------------------------- partial product: tensor memory -> shared
+            stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
+            stc_fence_after();
+            {
+                const int q = warp & 3, half = warp >> 2;
+                const int cbeg = half * (Npad / 2), cend = cbeg + Npad / 2;
+                for (int c0 = cbeg; c0 < cend; c0 += 8) {
+                    uint32_t r[8];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                                 : "r"(taddr) : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) partial[(c0 + i) * STC_BM + q * 32 + lane] = __uint_as_float(r[i]);
+                }
+            }
+            stc_fence_before();
+            stc_cluster_sync();      // all four partials of this (M tile, split) are in shared memory
+        }
+        // ------------------------------------------------------------ split-K reduction over DSMEM + epilogue
+#pragma unroll
+        for (int ci = 0; ci < 8; ++ci) {
+            const int c = warp + 8 * ci;
+            if (c >= Nc) continue;
+            const int b = b_lo + rank * Nc + c;
+            float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (s > 0) {
+                const uint32_t local = stc_smem_u32(partial + (rank * Nc + c) * STC_BM + 4 * lane);
+#pragma unroll
+                for (int q = 0; q < STC_CS; ++q) {
+                    const float4 p = stc_ld_cluster_f4(stc_map_to_cta(local, (uint32_t)q));
+                    sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+                }
+            }
+            if (b < B) {
+                float4 v;
+                v.x = pre_v[ci].x + sum.x; v.y = pre_v[ci].y + sum.y; v.z = pre_v[ci].z + sum.z; v.w = pre_v[ci].w + sum.w;
+                if (!bptt) {
+                    v.x = fminf(fmaxf(v.x, 0.f), a.maxAct); v.y = fminf(fmaxf(v.y, 0.f), a.maxAct);
+                    v.z = fminf(fmaxf(v.z, 0.f), a.maxAct); v.w = fminf(fmaxf(v.w, 0.f), a.maxAct);
+                } else {
+                    v.x = (act_v[ci].x > 0.f && act_v[ci].x < a.maxAct) ? v.x : 0.f;
+                    v.y = (act_v[ci].y > 0.f && act_v[ci].y < a.maxAct) ? v.y : 0.f;
+                    v.z = (act_v[ci].z > 0.f && act_v[ci].z < a.maxAct) ? v.z : 0.f;
+                    v.w = (act_v[ci].w > 0.f && act_v[ci].w < a.maxAct) ? v.w : 0.f;
+                }
+                if (t >= Tb[ci]) v = make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4 *>(out + ((int64_t)t * B + b) * H + j4) = v;
+            }
+        }
+        // ------------------------------------------------------------ publish S_t: one counter arrival per CTA
+        if (s + 1 < T) {
+            __syncthreads();
+            if (tid == 0) {
+                asm volatile("fence.proxy.async;" ::: "memory");
+                __threadfence();
+                atomicAdd(ctr, 1u);
+            }
+        }
+    }
+    // no CTA may exit while a peer can still read its shared memory
+    stc_fence_before();
+    stc_cluster_sync();
+    if (warp == 1) {
+        stc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(a.tmem_cols) : "memory");
+    }
+}
+
+// W^T (row-major H x H) for the BPTT A operand
+__global__ void stc_transpose_kernel(const float *__restrict__ w, float *__restrict__ wt, int H) {
+    __shared__ float tile[32][33];
+    const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = w[(int64_t)(r0 + i) * H + c0 + threadIdx.x];
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += 8) wt[(int64_t)(c0 + i) * H + r0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// ---------------------------------------------------------------------------------- host side
+typedef CUresult (*StcEncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static StcEncodeFn stc_encode() {
+    static StcEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (StcEncodeFn)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+struct StcPlan { int NS, Npad, stages, tmem_cols; uint32_t stage_bytes; size_t smem; };
+
+static int stc_max_clusters(size_t smem) {
+    static int cached = -1;
+    if (cached >= 0) return cached;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(STC_CS, 64, 2);
+    cfg.blockDim = dim3(STC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = STC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&n, sweep_tc_kernel, &cfg) != cudaSuccess) {
+        cudaGetLastError();
+        n = 0;
+    }
+    cached = n;
+    if (getenv("CTCB_DEBUG")) fprintf(stderr, "[ctcb] tensor-core sweep: max active clusters of %d CTAs = %d\n", STC_CS, n);
+    return cached;
+}
+
+static constexpr size_t STC_SMEM_MAX = 200 * 1024;      // operand ring budget (+ barriers) within the 227 KB per CTA
+
+static bool stc_plan(int H, int B, int ndir, StcPlan *p) {
+    if (H % 128 != 0 || H < 512 || B < 1) return false;
+    const int MT = H / STC_BM;
+    const int maxc = stc_max_clusters(STC_SMEM_MAX + 2048);
+    if (maxc < ndir * MT) return false;
+    int ns_cap = maxc / (ndir * MT);
+    static int ns_env = -1;
+    if (ns_env < 0) { const char *e = getenv("CTCB_SWEEP_TC_NS"); ns_env = e ? atoi(e) : 0; }
+    if (ns_env > 0 && ns_env < ns_cap) ns_cap = ns_env;
+    int NS = (B + 15) / 16;                  // never more splits than 16-utterance MMA tiles
+    if (NS > ns_cap) NS = ns_cap;
+    if (NS < 1) NS = 1;
+    int Npad = ((B + NS - 1) / NS + 15) / 16 * 16;
+    if (Npad > 256) return false;            // would need a second utterance group per CTA and step
+    NS = (B + Npad - 1) / Npad;              // drop splits that would be empty
+    p->NS = NS; p->Npad = Npad;
+    p->stage_bytes = 2 * STC_A_BYTES + 2 * (uint32_t)Npad * 128u;
+    int stages = (int)(STC_SMEM_MAX / p->stage_bytes);
+    if (stages > 6) stages = 6;
+    if (stages < 2) return false;
+    p->stages = stages;
+    int cols = 32;
+    while (cols < Npad) cols <<= 1;
+    p->tmem_cols = cols;
+    p->smem = (size_t)stages * p->stage_bytes + 512 + 1024;
+    return true;
+}
+
+static bool stc_enabled(int H) {
+    static int mode = -1;     // CTCB_SWEEP_TC=0 disables, =1 default (H >= 1024), =2 also H = 512
+    if (mode < 0) { const char *e = getenv("CTCB_SWEEP_TC"); mode = e ? atoi(e) : 1; }
+    if (mode == 0 || !stc_encode()) return false;
+    return H >= 1024 || (mode == 2 && H >= 512);
+}
+
+size_t sweep_tc_workspace_bytes(int H) { return (size_t)2 * H * H * sizeof(float) + 4096; }
+
+int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf, const float *Wb,
+                 float *outF, float *outB, const float *actF, const float *actB, float maxAct, unsigned int *counters,
+                 void *ws, size_t ws_bytes, cudaStream_t st, bool *handled) {
+    *handled = false;
+    const int ndir = Wb ? 2 : 1;
+    StcPlan p;
+    if (!stc_enabled(H) || !stc_plan(H, B, ndir, &p)) return CTCB_OK;
+    if (mode == 1 && (!ws || ws_bytes < sweep_tc_workspace_bytes(H))) return CTCB_OK;    // no room for W^T: other kernels
+    StcEncodeFn enc = stc_encode();
+    const float *A[2] = {Wf, Wb ? Wb : Wf};
+    if (mode == 1) {
+        float *wt = (float *)ws;
+        for (int d = 0; d < ndir; ++d) {
+            stc_transpose_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(A[d], wt + (size_t)d * H * H, H);
+            CTCB_LAUNCH_CHECK();
+            A[d] = wt + (size_t)d * H * H;
+        }
+        if (ndir == 1) A[1] = A[0];
+    }
+    float *outs[2] = {outF, Wb ? outB : outF};
+    CUtensorMap tmW[2], tmS[2];
+    for (int d = 0; d < 2; ++d) {
+        {
+            cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)H};
+            cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
+            cuuint32_t box[2] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM};
+            cuuint32_t es[2] = {1, 1};
+            CUresult r = enc(&tmW[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)A[d], dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(W) failed (%d)", (int)r);
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)T};
+            cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)B * H * sizeof(float)};
+            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)p.Npad, 1};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&tmS[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)outs[d], dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state) failed (%d)", (int)r);
+        }
+    }
+    SweepTcArgs a;
+    a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
+    a.out[0] = outs[0]; a.out[1] = outs[1]; a.act[0] = actF; a.act[1] = Wb ? actB : actF; a.maxAct = maxAct;
+    a.err = counters; a.counters = counters + 16;
+    a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
+    a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols;
+    CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * (size_t)(ndir * p.NS), st));
+    CTCB_CUDA_CHECK(cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(STC_CS, a.MT * p.NS, ndir);
+    cfg.blockDim = dim3(STC_THREADS);
+    cfg.dynamicSmemBytes = p.smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = STC_CS; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;       // co-residency of all CTAs (they meet at the counter barrier)
+    attr[1].val.cooperative = 1;
+    cfg.attrs = attr;
+    static int coop = -1;     // does this driver accept cluster + cooperative together?
+    if (coop != 0) {
+        cfg.numAttrs = 2;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], a);
+        if (e == cudaSuccess) { coop = 1; count_launch(); *handled = true; return CTCB_OK; }
+        cudaGetLastError();
+        if (coop == 1) return set_error(CTCB_ECUDA, "sweep_tc: launch failed: %s", cudaGetErrorString(e));
+        coop = 0;
+        if (getenv("CTCB_DEBUG")) fprintf(stderr, "[ctcb] tensor-core sweep: cooperative+cluster launch refused (%s), plain cluster launch\n", cudaGetErrorString(e));
+    }
+    cfg.numAttrs = 1;         // grid <= one wave of clusters by construction (stc_plan)
+    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], a));
+    count_launch();
+    *handled = true;
+    return CTCB_OK;
+}
+
+bool sweep_tc_would_run(int H, int B, int ndir) {
+    StcPlan p;
+    return stc_enabled(H) && stc_plan(H, B, ndir, &p);
+}
+
+}  // namespace ctcb
+
+extern "C" int ctcb_sweep_uses_tensor_cores(int H, int B) { return ctcb::sweep_tc_would_run(H, B, 2) ? 1 : 0; }

@@ -1,6 +1,6 @@
 """GPU unit test of the persistent recurrent sweep on its own (ctcb_brnn_sweep_f32) against a NumPy
 float64 restatement of brnnet.py:144-152 (forward) and :208-224 (BPTT), over layer sizes that take the
-register-resident path (H multiple of 128 up to 1024) and the generic path, full and partial
+register-resident path (H = 128/256/512), the tensor-core path (H >= 1024) and the generic path, full and partial
 utterance tiles, ragged lengths and the 20.0 clip."""
 import numpy as np
 import pytest
@@ -37,7 +37,11 @@ def _ref_bptt(d, Wf, Wb, F, Bk, lens, maxAct):
 
 @pytest.mark.parametrize("H,B,T", [(128, 8, 40), (128, 3, 33), (256, 9, 25), (512, 4, 30), (512, 32, 50),
                                      (1024, 16, 12), (96, 5, 20), (30, 2, 10), (64, 17, 21), (512, 16, 20),
-                                     (256, 64, 10)])
+                                     (256, 64, 10),
+                                     # the tensor-core kernel (sweep_tc.cu, H >= 1024): one and two utterance splits, partial
+                                     # 16-utterance tiles, the C3 / C4 per-GPU batch widths, H not a power of two
+                                     (1024, 128, 10), (1024, 40, 9), (1024, 3, 7), (2048, 32, 8), (2048, 256, 5),
+                                     (1536, 20, 6)])
 def test_sweep_forward_and_bptt(H, B, T, cuda):
     import _ctcb
     from _ctcb import lib, check, ptr
@@ -57,9 +61,10 @@ def test_sweep_forward_and_bptt(H, B, T, cuda):
     d_pre, d_Wf, d_Wb = dev(pre), dev(Wf), dev(Wb)
     d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
     oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty(T, B, H, device="cuda")
-    scratch = torch.zeros(1024, dtype=torch.int32, device="cuda")
+    nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
+    scratch = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
     check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(d_len), ptr(d_pre), ptr(d_Wf), ptr(d_Wb), ptr(oF), ptr(oB), None,
-                                  None, maxAct, ptr(scratch), _ctcb.current_stream()))
+                                  None, maxAct, ptr(scratch), nscr, _ctcb.current_stream()))
     torch.cuda.synchronize()
     assert scratch[:3].tolist() == [0, 0, 0], "error flag %s" % scratch[:3].tolist()
     gF, gB = oF.cpu().numpy().astype(np.float64), oB.cpu().numpy().astype(np.float64)
@@ -74,7 +79,7 @@ def test_sweep_forward_and_bptt(H, B, T, cuda):
     dF, dB = _ref_bptt(d, Wf, Wb, F32, B32, lens, maxAct)
     odF = torch.empty(T, B, H, device="cuda"); odB = torch.empty(T, B, H, device="cuda")
     check(lib.ctcb_brnn_sweep_f32(1, T, B, H, ptr(d_len), ptr(dev(d)), ptr(d_Wf), ptr(d_Wb), ptr(odF), ptr(odB),
-                                  ptr(oF), ptr(oB), maxAct, ptr(scratch), _ctcb.current_stream()))
+                                  ptr(oF), ptr(oB), maxAct, ptr(scratch), nscr, _ctcb.current_stream()))
     torch.cuda.synchronize()
     assert scratch[:3].tolist() == [0, 0, 0], "error flag %s" % scratch[:3].tolist()
     gdF, gdB = odF.cpu().numpy().astype(np.float64), odB.cpu().numpy().astype(np.float64)

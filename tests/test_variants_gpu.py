@@ -198,7 +198,7 @@ def test_unidirectional_sweep_c_abi(cuda):
     scratch = torch.zeros(1024, dtype=torch.int32, device="cuda")
     d_W = dev(W)
     check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(d_len), ptr(dev(pre)), ptr(d_W), None, ptr(oF), None, None, None,
-                                  20.0, ptr(scratch), _ctcb.current_stream()))
+                                  20.0, ptr(scratch), 4096, _ctcb.current_stream()))
     torch.cuda.synchronize()
     assert scratch[:3].tolist() == [0, 0, 0]
     gF = oF.cpu().numpy().astype(np.float64)
@@ -213,7 +213,7 @@ def test_unidirectional_sweep_c_abi(cuda):
             dF[t, b] = m[t, b] * (d[t, b] + (W.T @ dF[t + 1, b] if t + 1 < lens[b] else 0.0))
     odF = torch.empty(T, B, H, device="cuda")
     check(lib.ctcb_brnn_sweep_f32(1, T, B, H, ptr(d_len), ptr(dev(d)), ptr(d_W), None, ptr(odF), None, ptr(oF), None,
-                                  20.0, ptr(scratch), _ctcb.current_stream()))
+                                  20.0, ptr(scratch), 4096, _ctcb.current_stream()))
     torch.cuda.synchronize()
     assert scratch[:3].tolist() == [0, 0, 0]
     assert np.abs(odF.cpu().numpy() - dF).max() < 2e-4 * max(1.0, np.abs(dF).max())

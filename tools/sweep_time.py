@@ -13,10 +13,11 @@ Wb = (torch.rand(H, H, device="cuda", generator=g) * 2 - 1) * s
 pre = torch.randn(T, B, H, device="cuda", generator=g)
 lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
 oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty_like(oF); dF = torch.empty_like(oF); dB = torch.empty_like(oF)
-scr = torch.zeros(1024, dtype=torch.int32, device="cuda")
+nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
+scr = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
 st = _ctcb.current_stream()
-def fwd(): check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(oF), ptr(oB), None, None, 20.0, ptr(scr), st))
-def bwd(): check(lib.ctcb_brnn_sweep_f32(1, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(dF), ptr(dB), ptr(oF), ptr(oB), 20.0, ptr(scr), st))
+def fwd(): check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(oF), ptr(oB), None, None, 20.0, ptr(scr), nscr, st))
+def bwd(): check(lib.ctcb_brnn_sweep_f32(1, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(dF), ptr(dB), ptr(oF), ptr(oB), 20.0, ptr(scr), nscr, st))
 for _ in range(3): fwd(); bwd()
 torch.cuda.synchronize()
 for name, fn in (("fwd", fwd), ("bptt", bwd)):
@@ -24,6 +25,6 @@ for name, fn in (("fwd", fwd), ("bptt", bwd)):
     e0.record()
     for _ in range(20): fn()
     e1.record(); torch.cuda.synchronize()
-    print("%s sweep=%s nb=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
-        name, os.environ.get("CTCB_SWEEP", "auto"), os.environ.get("CTCB_SWEEP_NB", "auto"), T, B, H,
+    print("%s sweep=%s tc=%s nb=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
+        name, os.environ.get("CTCB_SWEEP", "auto"), os.environ.get("CTCB_SWEEP_TC", "auto"), os.environ.get("CTCB_SWEEP_NB", "auto"), T, B, H,
         e0.elapsed_time(e1) / 20, 1e3 * e0.elapsed_time(e1) / 20 / T, int(scr[0])))
