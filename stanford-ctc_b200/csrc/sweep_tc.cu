@@ -47,7 +47,14 @@ struct SweepTcArgs {
     int stages;
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
+    unsigned long long *trace;   // optional (CTCB_SWEEP_TRACE): [64 steps][16] SM clock stamps of CTA (0,0,0)
 };
+constexpr int STC_TRACE_STEPS = 64;
+#define STC_STAMP(slot)                                                                                         \
+    do {                                                                                                        \
+        if (a.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && s < STC_TRACE_STEPS)           \
+            a.trace[s * 16 + (slot)] = (unsigned long long)clock64();                                           \
+    } while (0)
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t stc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -215,6 +222,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 // ---------------------------------------------------- wait for S_{t-1}, then TMA producer
                 const unsigned int target = domain * (unsigned int)s;
                 unsigned int v;
+                STC_STAMP(0);
                 const long long t0 = clock64();
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -222,6 +230,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     if (clock64() - t0 > 2000000000LL) { *dead = 1; atomicExch(a.err, 3u); break; }
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
+                STC_STAMP(1);
                 for (int i = 0; i < nkb; ++i) {
                     const uint32_t g = it + (uint32_t)i;
                     const int st = (int)(g % (uint32_t)STAGES);
@@ -234,6 +243,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     stc_tma_2d(stc_smem_u32(sp), tmW, fb, k, m0);
                     stc_tma_3d(stc_smem_u32(sp + 2 * STC_A_BYTES), tmS, fb, k, b_lo, tprev);
                 }
+                STC_STAMP(2);
             } else if (warp == 1 && lane == 0) {
                 // ---------------------------------------------------- MMA issuer
                 const uint32_t idesc = stc_idesc(STC_BM, Npad);
@@ -243,6 +253,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     const uint32_t use = g / (uint32_t)STAGES;
                     stc_mbar_wait(stc_smem_u32(&ready[st]), use & 1, dead, a.err);
                     stc_fence_after();
+                    if (i == 0) STC_STAMP(3);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
                     const uint64_t dB = stc_smem_desc(sa + 2 * STC_A_BYTES), dBl = stc_smem_desc(sa + 2 * STC_A_BYTES + B_BYTES);
@@ -256,6 +267,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     stc_commit(stc_smem_u32(&empty[st]));
                 }
                 stc_commit(stc_smem_u32(done));
+                STC_STAMP(4);
             } else if (warp >= 4) {
                 // ---------------------------------------------------- splitters (128 threads)
                 const int stid = tid - 128;
@@ -264,6 +276,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
                     stc_mbar_wait(stc_smem_u32(&full[st]), use & 1, dead, a.err);
+                    if (i == 0 && stid == 0) STC_STAMP(11);
+                    if (i == nkb - 1 && stid == 0) STC_STAMP(12);
                     uint8_t *sp = base + (size_t)st * stage_bytes;
                     const float4 *hiA = reinterpret_cast<const float4 *>(sp);
                     float4 *loA = reinterpret_cast<float4 *>(sp + STC_A_BYTES);
@@ -291,6 +305,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             // -------------------------------------------------------- partial product: tensor memory -> shared
             stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
             stc_fence_after();
+            if (tid == 64) STC_STAMP(5);
             {
                 const int q = warp & 3, half = warp >> 2;
                 const int cbeg = half * (Npad / 2), cend = cbeg + Npad / 2;
@@ -306,7 +321,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
             }
             stc_fence_before();
+            if (tid == 64) STC_STAMP(6);
             stc_cluster_sync();      // all four partials of this (M tile, split) are in shared memory
+            if (tid == 64) STC_STAMP(7);
         }
         // ------------------------------------------------------------ split-K reduction over DSMEM + epilogue
 #pragma unroll
@@ -340,12 +357,15 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             }
         }
         // ------------------------------------------------------------ publish S_t: one counter arrival per CTA
+        if (tid == 64) STC_STAMP(8);
         if (s + 1 < T) {
             __syncthreads();
             if (tid == 0) {
+                STC_STAMP(9);
                 asm volatile("fence.proxy.async;" ::: "memory");
                 __threadfence();
                 atomicAdd(ctr, 1u);
+                STC_STAMP(10);
             }
         }
     }
@@ -447,7 +467,7 @@ static bool stc_enabled(int H) {
     return H >= 1024 || (mode == 2 && H >= 512);
 }
 
-size_t sweep_tc_workspace_bytes(int H) { return (size_t)2 * H * H * sizeof(float) + 4096; }
+size_t sweep_tc_workspace_bytes(int H) { return (size_t)2 * H * H * sizeof(float) + 4096 + STC_TRACE_STEPS * 16 * 8; }
 
 int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf, const float *Wb,
                  float *outF, float *outB, const float *actF, const float *actB, float maxAct, unsigned int *counters,
@@ -498,6 +518,13 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     a.err = counters; a.counters = counters + 16;
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols;
+    a.trace = nullptr;
+    {
+        static int trace_env = -1;
+        if (trace_env < 0) trace_env = getenv("CTCB_SWEEP_TRACE") ? 1 : 0;
+        if (trace_env && ws && ws_bytes >= sweep_tc_workspace_bytes(H))
+            a.trace = (unsigned long long *)((char *)ws + (size_t)2 * H * H * sizeof(float) + 4096);
+    }
     CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * (size_t)(ndir * p.NS), st));
     CTCB_CUDA_CHECK(cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
     cudaLaunchConfig_t cfg{};

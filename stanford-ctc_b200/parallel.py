@@ -41,6 +41,33 @@ def select_step_utterances(data_dict, alis, chunk, max_frames, rank, world, log=
     return shard(used, rank, world)
 
 
+def bucketed_chunks(keys, length_of, batch_size, pool_batches=16, rng=None):
+    """Minibatches of similar length from an already shuffled key list (the reference steps one
+    utterance at a time, sgd.py:68-70, so it never pads).  The shuffled list is cut into pools of
+    pool_batches * batch_size keys; each pool is sorted by length and cut into minibatches, and the minibatches of a
+    pool are visited in random order -- every key is used exactly once per call, the padding of a step drops from
+    max/mean over the corpus to max/mean over ~1/pool_batches of it.  batch_size == 1 returns the shuffled order
+    unchanged (the reference's schedule).  Returns (chunks, padded_frames, real_frames)."""
+    if batch_size <= 1:
+        ks = list(keys)
+        n = sum(length_of(k) for k in ks)
+        return [[k] for k in ks], n, n
+    import random as _random
+    rng = rng or _random
+    chunks, padded, real = [], 0, 0
+    pool = max(1, pool_batches) * batch_size
+    for p0 in range(0, len(keys), pool):
+        part = sorted(keys[p0:p0 + pool], key=length_of)
+        cs = [part[i:i + batch_size] for i in range(0, len(part), batch_size)]
+        rng.shuffle(cs)
+        for c in cs:
+            ls = [length_of(k) for k in c]
+            padded += max(ls) * len(ls)
+            real += sum(ls)
+        chunks.extend(cs)
+    return chunks, padded, real
+
+
 def per_rank_capacity(batch_size, world):
     """Utterance capacity each rank must allocate for a global step of batch_size utterances."""
     return (batch_size + world - 1) // max(world, 1)

@@ -27,7 +27,7 @@ import parallel
 class SGD:
 
     def __init__(self, model, maxBatch, alpha=1e-2, optimizer='nesterov',
-                 momentum=0.9, maxGradNorm=1500, batchSize=1, verbose=True):
+                 momentum=0.9, maxGradNorm=1500, batchSize=1, verbose=True, bucketPool=16):
         torch = _ctcb.require_cuda()
         self._torch = torch
         self.model = model
@@ -39,6 +39,11 @@ class SGD:
         self.maxGNorm = maxGradNorm  # gradient clip norm value
         self.batchSize = batchSize
         self.verbose = verbose
+        # length-bucketed minibatches: pools of bucketPool * batchSize shuffled utterances sorted by length (0 = plain
+        # chunks of the shuffled list); padded_frames / real_frames accumulate what the padding costs
+        self.bucketPool = bucketPool
+        self.padded_frames = 0
+        self.real_frames = 0
         # the reference's adagrad branch is dead code (`assert False`, sgd.py:24-26)
         assert self.optimizer == 'nesterov', "only the nesterov optimizer exists (sgd.py:24-26)"
 
@@ -201,7 +206,15 @@ class SGD:
         random.shuffle(keys)
 
         step = max(1, self.batchSize)
-        chunks = [keys[k0:k0 + step] for k0 in range(0, len(keys), step)]
+        if self.bucketPool > 0:
+            # minibatches of similar length (every rank draws the same chunks: same seed, same shuffled list)
+            chunks, padded, real = parallel.bucketed_chunks(keys, lambda k: data_dict[k].shape[1], step, self.bucketPool)
+        else:
+            chunks = [keys[k0:k0 + step] for k0 in range(0, len(keys), step)]
+            ls = [[data_dict[k].shape[1] for k in c] for c in chunks]
+            padded, real = sum(max(l) * len(l) for l in ls if l), sum(sum(l) for l in ls)
+        self.padded_frames += padded
+        self.real_frames += real
         if not chunks:
             return
         # the host is always one step ahead of the device: step i+1 is packed, uploaded and enqueued while step i

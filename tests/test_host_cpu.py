@@ -164,3 +164,32 @@ def test_step_utterance_selection_is_consistent_across_ranks():
         assert shards[0] == ok[0::world]
         assert all(l == logs[0] for l in logs) and len(logs[0]) == len(keys) - len(ok)
         assert any("exceeds batch length" in m for m in logs[0]) and any("less than label length" in m for m in logs[0])
+
+
+def test_length_bucketed_chunks_cover_every_key_once_and_cut_padding():
+    import random
+    import parallel
+    rng = random.Random(5)
+    lens = {("k%d" % i): rng.randint(160, 240) for i in range(1000)}      # the +-20 % ragged-T variant of SURVEY 8d
+    keys = list(lens)
+    rng.shuffle(keys)
+    chunks, padded, real = parallel.bucketed_chunks(keys, lens.get, 32, 16, rng=random.Random(1))
+    flat = [k for c in chunks for k in c]
+    assert sorted(flat) == sorted(keys) and all(len(c) <= 32 for c in chunks)
+    plain = [keys[i:i + 32] for i in range(0, len(keys), 32)]
+    plain_padded = sum(max(lens[k] for k in c) * len(c) for c in plain)
+    assert real == sum(lens.values())
+    assert padded < plain_padded and (padded - real) < 0.25 * (plain_padded - real)     # most of the padding is gone
+    # batch size 1 is the reference's schedule: the shuffled order, untouched
+    one, p1, r1 = parallel.bucketed_chunks(keys, lens.get, 1)
+    assert [c[0] for c in one] == keys and p1 == r1
+
+
+def test_label_capacity_admission():
+    import numpy as np
+    import parallel
+    dd = {"a": np.zeros((3, 50)), "b": np.zeros((3, 50)), "c": np.zeros((3, 10))}
+    alis = {"a": list(range(40)), "b": list(range(12)), "c": list(range(12))}
+    logs = []
+    used = parallel.select_step_utterances(dd, alis, ["a", "b", "c"], 60, 0, 1, log=logs.append, max_labels=20)
+    assert used == ["b"] and len(logs) == 2          # "a": too many labels for the buffers; "c": fewer frames than labels

@@ -19,7 +19,8 @@ dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
 oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty_like(oF)
 nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
 scr = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
-check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(dev(lens)), ptr(dev(pre)), ptr(dev(Wf)), ptr(dev(Wb)), ptr(oF), ptr(oB), None, None,
+d_lens, d_pre, d_Wf, d_Wb = dev(lens), dev(pre), dev(Wf), dev(Wb)       # keep the device copies alive
+check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(d_lens), ptr(d_pre), ptr(d_Wf), ptr(d_Wb), ptr(oF), ptr(oB), None, None,
                               20.0, ptr(scr), nscr, _ctcb.current_stream()))
 torch.cuda.synchronize()
 g = oF.cpu().numpy().astype(np.float64)

@@ -28,3 +28,19 @@ for name, fn in (("fwd", fwd), ("bptt", bwd)):
     print("%s sweep=%s tc=%s nb=%s T=%d B=%d H=%d: %.3f ms/launch (%.2f us/step) flag=%d" % (
         name, os.environ.get("CTCB_SWEEP", "auto"), os.environ.get("CTCB_SWEEP_TC", "auto"), os.environ.get("CTCB_SWEEP_NB", "auto"), T, B, H,
         e0.elapsed_time(e1) / 20, 1e3 * e0.elapsed_time(e1) / 20 / T, int(scr[0])))
+
+if os.environ.get("CTCB_SWEEP_TRACE"):
+    off = (4096 + 2 * H * H * 4 + 4096) // 8
+    tr = scr.view(torch.int64)[off:off + 64 * 16].cpu().numpy().reshape(64, 16)
+    names = ["step top", "counter seen", "TMA issued", "first ready (MMA)", "done commit issued", "done seen (epi)",
+             "partial in smem", "after cluster sync", "after finalize stores", "after syncthreads", "after arrive",
+             "first full (splitter)", "last full (splitter)"]
+    import numpy as np
+    rows = tr[8:56]
+    base = rows[:, 0:1]
+    rel = (rows[:, :13] - base).astype(np.float64)
+    med = np.median(rel, axis=0)
+    period = np.median(np.diff(tr[8:56, 0]))
+    print("trace of CTA (0,0,0), last launch (BPTT), SM cycles relative to the step top, median over steps 8..55; step period %.0f cycles" % period)
+    for i in np.argsort(med):
+        print("  %-24s %8.0f" % (names[i], med[i]))
