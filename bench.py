@@ -347,22 +347,28 @@ def _time_device_steps(torch, dist, world, opt, batch, steps, warmup, flush):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(warmup, 3)):
-        opt.it += 1
-        opt.step_device(batch, opt._momentum_now())
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-    launches0 = lib.ctcb_launch_count()
-    barrier()
-    t0 = time.perf_counter()
-    for s_ in range(steps):
-        flush.zero_()                                  # L2 flush between timed steps (untimed)
-        opt.it += 1
-        ev[s_][0].record()
-        opt.step_device(batch, opt._momentum_now())
-        ev[s_][1].record()
-    barrier()
-    wall = time.perf_counter() - t0
+    # a stream of our own: the step is replayed as ONE CUDA graph launch from its third occurrence on (sgd.SGD.step_device),
+    # and the legacy default stream cannot be captured.  Events are recorded on this (the launching) stream.
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    opt.it = max(opt.it, 11)                           # past the momentum warm-up (sgd.py:64-74): one graph, not two
+    with torch.cuda.stream(stream):
+        for _ in range(max(warmup, 3)):
+            opt.it += 1
+            opt.step_device(batch, opt._momentum_now())
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        launches0 = lib.ctcb_launch_count()
+        barrier()
+        t0 = time.perf_counter()
+        for s_ in range(steps):
+            flush.zero_()                                  # L2 flush between timed steps (untimed)
+            opt.it += 1
+            ev[s_][0].record()
+            opt.step_device(batch, opt._momentum_now())
+            ev[s_][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
     launches = (lib.ctcb_launch_count() - launches0) / float(steps)
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     tt = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
@@ -378,10 +384,12 @@ def _phase_profile(torch, dist, world, rank, opt, batch, flush, nprof):
     from _ctcb import lib
     if rank == 0:
         lib.ctcb_profile_enable(1)
+    graphs, opt.useGraphs = opt.useGraphs, False       # the per-phase events need the eager launch sequence
     for _ in range(nprof):
         flush.zero_()
         opt.it += 1
         opt.step_device(batch, opt._momentum_now())
+    opt.useGraphs = graphs
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -638,6 +646,7 @@ def run_ours(args, c):
             "data": "synthetic",
             "config": {"workload": c["name"], "global_batch": Bg, "per_gpu_batch": Bl, "seq_len": c["T"],
                        "parallelism": "dp%d" % world, "l2": "flushed between timed steps (256 MiB write, untimed)",
+                       "launch": "one CUDA graph per step (captured from the step's own launch sequence)",
                        "optimizer": "nesterov, maxGradNorm=1500, step=1e-5",
                        "flops_per_utt": flops_per_utt(c)},
             "e2e": {"value": e2e_value, "unit": "utterances/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 32,

@@ -184,6 +184,18 @@ int ctcb_sumsq_f32(const float *g, int64_t n, float *gnorm2_out, void *scratch, 
 int ctcb_sgd_nesterov_step_f32(float *w, float *v, const float *g, int64_t n, float mom, float alpha,
                                float max_gnorm, const float *gnorm2, const float *n_valid, void *stream);
 
+/* ---- CUDA graphs: replay one optimisation step (the reference issues ~16(N+3)+8(T-1) launches per utterance,
+ *      sgd.py:91-161 + brnnet.py:117-249; this library ~40 per minibatch) as ONE graph launch -----------------------
+ * Between begin and end, calls into this library on `stream` are captured instead of executed (including the internal
+ * side stream and the NCCL exchange); every pointer, size and scalar argument is frozen into the graph, so a graph is
+ * valid for one (buffers, B, Tmax, momentum, step size) combination.  Warm the same calls up once before capturing
+ * (first-use initialisation is not capturable). */
+typedef struct ctcb_graph ctcb_graph;
+int ctcb_graph_capture_begin(void *stream);
+int ctcb_graph_capture_end(void *stream, ctcb_graph **out);
+int ctcb_graph_launch(ctcb_graph *g, void *stream);
+void ctcb_graph_destroy(ctcb_graph *g);
+
 /* ---- data-parallel exchange (the reference's only device hook is CUDA_DEVICE,
  *      ctc_fast/runNNet.py:117-120, and it has no multi-GPU path) -------------------------------------
  * One process per GPU.  Rank 0 obtains an id (HOST buffer of CTCB_COMM_ID_BYTES) and hands it to the other ranks by

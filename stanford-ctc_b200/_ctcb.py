@@ -68,6 +68,10 @@ _PROTOS = {
     "ctcb_allreduce_grads": (c_int, [c_vp, c_vp, c_i64, c_vp]),
     "ctcb_brnn_set_comm": (c_int, [c_vp, c_vp]),
     "ctcb_brnn_exchange_only": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "ctcb_graph_capture_begin": (c_int, [c_vp]),
+    "ctcb_graph_capture_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "ctcb_graph_launch": (c_int, [c_vp, c_vp]),
+    "ctcb_graph_destroy": (None, [c_vp]),
     "ctcb_axpy_f32": (c_int, [c_vp, c_vp, c_f32, c_i64, c_vp]),
     "ctcb_sumsq_f32": (c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "ctcb_sgd_nesterov_step_f32": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f32, c_f32, c_f32, c_vp, c_vp, c_vp]),

@@ -3,6 +3,7 @@
 #include <stdarg.h>
 #include <string.h>
 #include <map>
+#include <new>
 #include <string>
 #include <vector>
 
@@ -82,3 +83,55 @@ extern "C" int ctcb_profile_report(char *buf, size_t cap) {
 extern "C" int ctcb_version(void) { return 100; }
 extern "C" const char *ctcb_last_error(void) { return ctcb::g_last_error; }
 extern "C" uint64_t ctcb_launch_count(void) { return ctcb::g_launch_count.load(); }
+
+// ---- CUDA graphs: one optimisation step (dozens of small launches on two streams) replayed as ONE graph launch ----
+struct ctcb_graph {
+    cudaGraphExec_t exec;
+    uint64_t launches;     // kernels the captured region launched (ctcb_launch_count stays meaningful under replay)
+};
+static thread_local uint64_t g_capture_launch0 = 0;
+
+extern "C" int ctcb_graph_capture_begin(void *stream) {
+    using namespace ctcb;
+    // ThreadLocal: other threads of the host program (loaders, other GPUs' drivers) stay free to call CUDA
+    CTCB_CUDA_CHECK(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    g_capture_launch0 = g_launch_count.load();
+    return CTCB_OK;
+}
+
+extern "C" int ctcb_graph_capture_end(void *stream, ctcb_graph **out) {
+    using namespace ctcb;
+    if (!out) return set_error(CTCB_EINVAL, "ctcb_graph_capture_end: null output");
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture((cudaStream_t)stream, &g);
+    if (e != cudaSuccess || !g) {
+        cudaGetLastError();
+        return set_error(CTCB_ECUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    }
+    ctcb_graph *h = new (std::nothrow) ctcb_graph;
+    if (!h) { cudaGraphDestroy(g); return set_error(CTCB_ENOMEM, "ctcb_graph_capture_end: out of host memory"); }
+    h->launches = g_launch_count.load() - g_capture_launch0;
+    g_launch_count.fetch_sub(h->launches);      // nothing ran during capture
+    e = cudaGraphInstantiate(&h->exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        delete h;
+        return set_error(CTCB_ECUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    *out = h;
+    return CTCB_OK;
+}
+
+extern "C" int ctcb_graph_launch(ctcb_graph *h, void *stream) {
+    using namespace ctcb;
+    if (!h) return set_error(CTCB_EINVAL, "ctcb_graph_launch: null graph");
+    CTCB_CUDA_CHECK(cudaGraphLaunch(h->exec, (cudaStream_t)stream));
+    count_launch((int)h->launches);
+    return CTCB_OK;
+}
+
+extern "C" void ctcb_graph_destroy(ctcb_graph *h) {
+    if (!h) return;
+    cudaGraphExecDestroy(h->exec);
+    delete h;
+}

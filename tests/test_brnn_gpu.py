@@ -212,3 +212,35 @@ def test_check_grad_finite_differences(cuda):
     pairs = nn.check_grad(datas[0], labelss[0], epsilon=1e-2, maxChecks=2, verbose=False)
     ana = np.array([p[0] for p in pairs]); num = np.array([p[1] for p in pairs])
     assert np.abs(ana - num).max() < 0.05 * max(1.0, np.abs(ana).max())
+
+
+def test_graph_replayed_steps_equal_eager_steps(cuda):
+    """sgd.SGD.step_device captures the step into a CUDA graph on its third occurrence and replays it: six steps with
+    graphs must leave bit-identical parameters to six eager steps, and the library's launch counter keeps counting."""
+    import nnets.brnnet as rnnet
+    import sgd
+    from _ctcb import lib
+    torch = cuda
+    D, K, H, N, B = 13, 11, 128, 2, 4
+    datas, labelss = recipes.synth_batch(D, K, [25, 30, 18, 30], [6, 8, 4, 9], seed=9)
+    outs = []
+    for use in (False, True):
+        np.random.seed(2)
+        nn = rnnet.NNet(D, K, H, N, 30, temporalLayer=1, maxUtts=B, maxLabels=10)
+        nn.initParams()
+        opt = sgd.SGD(nn, 30, alpha=1e-3, momentum=0.9, maxGradNorm=5.0, batchSize=B, verbose=False)
+        opt.useGraphs = use
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            nn._batch.pack(datas, labelss).upload()
+            n0 = lib.ctcb_launch_count()
+            for it in range(6):
+                opt.it = 20 + it
+                opt.step_device(nn._batch, 0.9)
+            per_step = (lib.ctcb_launch_count() - n0) / 6.0
+        st.synchronize()
+        assert (len(opt._graphs) == 1) == use
+        outs.append((nn.params.clone(), per_step))
+    assert bool((outs[0][0] == outs[1][0]).all())
+    assert outs[0][1] == outs[1][1] and outs[0][1] > 10
