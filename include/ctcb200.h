@@ -160,10 +160,10 @@ int ctcb_brnn_apply_l2_f32(ctcb_brnn *h, const float *params, float *grads, void
  * mode 1: outF[t] = within(actF[t]) * (pre[t] + outF[t+1].Wf), outB mirrored.
  * Wb == NULL (with outB/actB ignored) runs the forward-in-time direction alone: the uni-directional layer of
  * nnets/rnnet.py:112-116 [mode 0] and :162-177 [mode 1].
- * scratch: device memory, >= 4096 bytes (word 0 = error flag, cleared by the call); with
- * ctcb_brnn_sweep_workspace_bytes(H) bytes the tensor-core kernel (H >= 1024, sweep_tc.cu) can also run mode 1, which
- * needs room for the transposed recurrent matrices. */
-size_t ctcb_brnn_sweep_workspace_bytes(int H);
+ * scratch: 256-byte aligned device memory, >= 4096 bytes (word 0 = error flag, cleared by the call); the tensor-core
+ * kernel (H >= 1024, sweep_tc.cu) additionally needs room for the (hi, lo) stacks of the recurrent matrices and the
+ * ring of state low halves: ctcb_brnn_sweep_workspace_bytes(H, B) in total, else the FFMA kernels run. */
+size_t ctcb_brnn_sweep_workspace_bytes(int H, int B);
 int ctcb_brnn_sweep_f32(int mode, int T, int B, int H, const int32_t *T_per_utt, const float *pre,
                         const float *Wf, const float *Wb, float *outF, float *outB, const float *actF,
                         const float *actB, float maxAct, void *scratch, size_t scratch_bytes, void *stream);

@@ -56,7 +56,7 @@ _PROTOS = {
                                         c_vp, c_vp, c_vp, c_sz, c_vp]),
     "ctcb_brnn_sweep_f32": (c_int, [c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_f32,
                                     c_vp, c_sz, c_vp]),
-    "ctcb_brnn_sweep_workspace_bytes": (c_sz, [c_int]),
+    "ctcb_brnn_sweep_workspace_bytes": (c_sz, [c_int, c_int]),
     "ctcb_sweep_uses_tensor_cores": (c_int, [c_int, c_int]),
     "ctcb_brnn_set_deferred_l2": (c_int, [c_vp, c_int]),
     "ctcb_brnn_apply_l2_f32": (c_int, [c_vp, c_vp, c_vp, c_vp]),

@@ -22,7 +22,7 @@ namespace ctcb {
 int run_sweep(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf,
               const float *Wb, float *outF, float *outB, const float *actF, const float *actB, float maxAct,
               unsigned int *counters, void *ws, size_t ws_bytes, cudaStream_t st);
-size_t sweep_tc_workspace_bytes(int H);
+size_t sweep_tc_workspace_bytes(int H, int B);
 int run_add2(const float *x, const float *y, float *z, int64_t n, cudaStream_t st);
 int run_sumsq(const float *g, int64_t n, float *out, float scale, int accumulate, void *scratch, cudaStream_t st);
 int comm_allreduce_ranges(ctcb_comm *c, float *const *ptrs, const int64_t *counts, int k, cudaStream_t st);
@@ -213,7 +213,7 @@ WsLayout ws_layout(const ctcb_brnn_config *c) {
     w.colsum2 = take(((R + CS_ROWS - 1) / CS_ROWS) * wide * sizeof(float));
     w.scratch = take(8192);
     w.counters = take(sizeof(unsigned int) * 1024);
-    w.sweep_bytes = eff_tl(c) ? sweep_tc_workspace_bytes(H) : 0;
+    w.sweep_bytes = eff_tl(c) ? sweep_tc_workspace_bytes(H, c->maxB) : 0;
     w.sweep = take(w.sweep_bytes);
     w.total = off;
     return w;
@@ -548,4 +548,4 @@ extern "C" int ctcb_brnn_exchange_only(ctcb_brnn *h, const float *params, float 
     return CTCB_OK;
 }
 
-extern "C" size_t ctcb_brnn_sweep_workspace_bytes(int H) { return 4096 + ctcb::sweep_tc_workspace_bytes(H); }
+extern "C" size_t ctcb_brnn_sweep_workspace_bytes(int H, int B) { return 4096 + ctcb::sweep_tc_workspace_bytes(H, B); }

@@ -9,8 +9,9 @@
 //   * work split: M tiles of 128 output units x 4 K-slices (H/4 inputs each) x NS utterance splits x 2 directions
 //     = 128 CTAs at H = 1024 (NS = 2) and H = 2048 (NS = 1); one persistent CTA per SM for the whole sweep;
 //   * the 4 K-slices of an (M tile, utterance split, direction) form a CLUSTER: each CTA accumulates its partial
-//     product in tensor memory (tcgen05.mma.kind::tf32, operands staged by TMA into a 128B-swizzled ring, low halves
-//     produced on chip by splitter warps), copies it to its own shared memory, and after one cluster barrier CTA r
+//     product in tensor memory (tcgen05.mma.kind::tf32; hi AND lo halves of both operands arrive by TMA in a
+//     128B-swizzled ring: W's are prepared once per launch, the state's are written by the previous step's epilogue,
+//     so no thread touches the operands), copies it to its own shared memory, and after one cluster barrier CTA r
 //     sums the four partials of ITS quarter of the utterances through distributed shared memory
 //     (ld.shared::cluster), adds pre_t, applies clip / mask and writes S_t -- a deterministic split-K reduction
 //     that never touches global memory;
@@ -20,7 +21,10 @@
 //     hi + lo halves of both directions (67 MB) exceed the 33 MB of shared memory on the device, so residency is
 //     not an option there, and the stream is hidden behind the MMAs whenever the batch is large enough.
 //
-// BPTT needs W^T as the A operand: a transposed copy is made once per launch (2 H^2 floats of caller scratch).
+// Measured on B200 (tools/micro/umma_rate.cu): a kind::tf32 MMA costs max(45, N/2) cycles whatever M is, so the
+// recurrent matrix is the M = 128 operand and the utterances are N; a first version that produced the low halves with
+// splitter warps spent ~1300 cycles per k-block there (2.4x the 12 MMAs) -- hence the TMA-only operand path.
+// Scratch: the (hi, lo) stacks of W (W^T for BPTT) for both directions and the two-slot ring of state low halves.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>
@@ -38,6 +42,7 @@ struct SweepTcArgs {
     const int32_t *Tlen;
     const float *pre;
     float *out[2];
+    float *ring[2];           // [2][B][H] per direction: low halves (x - tf32(x)) of the last two states
     const float *act[2];
     float maxAct;
     unsigned int *err;        // [0]: set to 3 when a wait timed out (results invalid, never a hang)
@@ -47,6 +52,7 @@ struct SweepTcArgs {
     int stages;
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
+    int partial_own;          // 1: the partial product has its own shared-memory region (W prefetch across steps)
     unsigned long long *trace;   // optional (CTCB_SWEEP_TRACE): [64 steps][16] SM clock stamps of CTA (0,0,0)
 };
 constexpr int STC_TRACE_STEPS = 64;
@@ -137,24 +143,31 @@ __device__ __forceinline__ uint32_t stc_idesc(int m, int n) {
 
 // ---------------------------------------------------------------------------------------------------
 // grid = (4 K-slices [cluster], MT * NS, ndir); 8 warps:
-//   warp 0 lane 0 : waits for the previous step's state (counter barrier), then TMA producer;
-//   warp 1 lane 0 : MMA issuer (owns the tensor-memory allocation);
-//   warps 4..7    : splitters (lo = x - tf32(x) of every landed tile, in shared memory);
-//   all 8 warps   : tensor memory -> shared partial, cluster barrier, split-K reduction over DSMEM, epilogue.
+//   warp 0 lane 0 : TMA producer -- W (hi+lo stack, one 3-D box) as soon as a ring slot is free, even across the step
+//                   boundary; the state tiles (hi from the output array, lo from the ring) once the counter barrier
+//                   of the previous step has been seen;
+//   warp 1 lane 0 : MMA issuer (owns the tensor-memory allocation): 4 k-steps x 3 products per k-block;
+//   all 8 warps   : tensor memory -> shared partial, cluster barrier, split-K reduction over DSMEM, epilogue
+//                   (state, its low half for the next step, one counter arrival per CTA).
+// There is no generic-proxy write into the operand ring: both halves of both operands arrive by TMA.
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STC_THREADS, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
-                const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1, SweepTcArgs a) {
+                const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
+                const __grid_constant__ CUtensorMap tmL0, const __grid_constant__ CUtensorMap tmL1, SweepTcArgs a) {
     extern __shared__ __align__(1024) uint8_t stc_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)stc_smem + 1023) & ~(uintptr_t)1023);
     const int STAGES = a.stages;
     const uint32_t stage_bytes = a.stage_bytes;
     const uint32_t B_BYTES = (uint32_t)a.Npad * 128u;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(base + (size_t)STAGES * stage_bytes);
-    uint64_t *full = bars, *ready = bars + 8, *empty = bars + 16, *done = bars + 24;
+    uint8_t *after_ring = base + (size_t)STAGES * stage_bytes;
+    // the partial product [Npad][128] has a region of its own when it fits (then W tiles of the NEXT step may land in
+    // the ring while peers still read this CTA's partial); otherwise it aliases the ring and nothing is prefetched
+    float *partial = reinterpret_cast<float *>(a.partial_own ? after_ring : base);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(after_ring + (a.partial_own ? (size_t)a.Npad * 512 : 0));
+    uint64_t *fullW = bars, *fullS = bars + 8, *empty = bars + 16, *done = bars + 24;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 25);
     volatile int *dead = reinterpret_cast<volatile int *>(tmem_slot + 1);
-    float *partial = reinterpret_cast<float *>(base);                 // [Npad][128], aliases the operand ring
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int rank = blockIdx.x;                                      // K-slice = rank in cluster
@@ -168,15 +181,17 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     const bool ascending = (dir == 0) != bptt;
     const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
     const CUtensorMap *tmS = dir ? &tmS1 : &tmS0;
+    const CUtensorMap *tmL = dir ? &tmL1 : &tmL0;
     float *out = a.out[dir];
+    float *ring = a.ring[dir];                                        // [2][B][H]: low halves of the last two states
     const float *act = a.act[dir];
     unsigned int *ctr = a.counters + (dir * a.NS + ns);
     const unsigned int domain = (unsigned int)(STC_CS * a.MT);        // CTAs that share this counter
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            stc_mbar_init(stc_smem_u32(&full[s]), 1);
-            stc_mbar_init(stc_smem_u32(&ready[s]), 4);
+            stc_mbar_init(stc_smem_u32(&fullW[s]), 1);
+            stc_mbar_init(stc_smem_u32(&fullS[s]), 1);
             stc_mbar_init(stc_smem_u32(&empty[s]), 1);
         }
         stc_mbar_init(stc_smem_u32(done), 1);
@@ -195,7 +210,18 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
 
     // epilogue role: warp w takes columns c = w, w + 8, ... < Nc of this CTA's quarter; lane l owns units 4l..4l+3
     const int j4 = m0 + 4 * lane;
-    uint32_t it = 0;              // running k-block index of the ring (all roles advance it identically)
+    // ring bookkeeping in units of k-block jobs g = (s - 1) * nkb + i (s = 1 .. T-1): stage g % STAGES, use g / STAGES
+    uint32_t gW = 0;              // producer: next job whose W tiles have not been requested yet
+    uint32_t gM = 0;              // MMA issuer: next job to multiply
+
+    // issue the W tiles (hi + lo in one 3-D box) of job g; the caller guarantees the slot is free
+    auto issue_W = [&](uint32_t g) {
+        const int st = (int)(g % (uint32_t)STAGES);
+        const uint32_t fb = stc_smem_u32(&fullW[st]);
+        stc_mbar_expect_tx(fb, 2 * STC_A_BYTES);
+        const int i = (int)(g % (uint32_t)nkb);
+        stc_tma_3d(stc_smem_u32(base + (size_t)st * stage_bytes), tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);
+    };
 
     for (int s = 0; s < T; ++s) {
         const int t = ascending ? s : T - 1 - s;
@@ -218,11 +244,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             }
         }
         if (s > 0) {
+            const uint32_t g0 = (uint32_t)(s - 1) * (uint32_t)nkb, g1 = g0 + (uint32_t)nkb;
             if (warp == 0 && lane == 0) {
-                // ---------------------------------------------------- wait for S_{t-1}, then TMA producer
+                // ---------------------------------------------------- TMA producer
+                STC_STAMP(0);
                 const unsigned int target = domain * (unsigned int)s;
                 unsigned int v;
-                STC_STAMP(0);
                 const long long t0 = clock64();
                 do {
                     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
@@ -231,81 +258,60 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
                 STC_STAMP(1);
-                for (int i = 0; i < nkb; ++i) {
-                    const uint32_t g = it + (uint32_t)i;
+                for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                    const uint32_t fb = stc_smem_u32(&full[st]);
-                    stc_mbar_expect_tx(fb, STC_A_BYTES + B_BYTES);
-                    uint8_t *sp = base + (size_t)st * stage_bytes;
-                    const int k = (rank * nkb + i) * STC_BK;
-                    stc_tma_2d(stc_smem_u32(sp), tmW, fb, k, m0);
-                    stc_tma_3d(stc_smem_u32(sp + 2 * STC_A_BYTES), tmS, fb, k, b_lo, tprev);
+                    if (g >= gW) {            // W not prefetched: wait for the slot, then request it
+                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                        issue_W(g);
+                        gW = g + 1;
+                    }
+                    const uint32_t fb = stc_smem_u32(&fullS[st]);
+                    stc_mbar_expect_tx(fb, 2 * B_BYTES);
+                    uint8_t *sp = base + (size_t)st * stage_bytes + 2 * STC_A_BYTES;
+                    const int k = (rank * nkb + (int)(g - g0)) * STC_BK;
+                    stc_tma_3d(stc_smem_u32(sp), tmS, fb, k, b_lo, tprev);
+                    stc_tma_3d(stc_smem_u32(sp + B_BYTES), tmL, fb, k, b_lo, (s - 1) & 1);
                 }
                 STC_STAMP(2);
             } else if (warp == 1 && lane == 0) {
                 // ---------------------------------------------------- MMA issuer
                 const uint32_t idesc = stc_idesc(STC_BM, Npad);
-                for (int i = 0; i < nkb; ++i) {
-                    const uint32_t g = it + (uint32_t)i;
+                for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    stc_mbar_wait(stc_smem_u32(&ready[st]), use & 1, dead, a.err);
+                    stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
+                    stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
                     stc_fence_after();
-                    if (i == 0) STC_STAMP(3);
+                    if (g == g0) STC_STAMP(3);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
                     const uint64_t dB = stc_smem_desc(sa + 2 * STC_A_BYTES), dBl = stc_smem_desc(sa + 2 * STC_A_BYTES + B_BYTES);
 #pragma unroll
                     for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
                         const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-                        stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                        stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
-                        stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                        stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                        stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                               // hi . lo
+                        stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
                     }
                     stc_commit(stc_smem_u32(&empty[st]));
                 }
                 stc_commit(stc_smem_u32(done));
                 STC_STAMP(4);
-            } else if (warp >= 4) {
-                // ---------------------------------------------------- splitters (128 threads)
-                const int stid = tid - 128;
-                for (int i = 0; i < nkb; ++i) {
-                    const uint32_t g = it + (uint32_t)i;
-                    const int st = (int)(g % (uint32_t)STAGES);
-                    const uint32_t use = g / (uint32_t)STAGES;
-                    stc_mbar_wait(stc_smem_u32(&full[st]), use & 1, dead, a.err);
-                    if (i == 0 && stid == 0) STC_STAMP(11);
-                    if (i == nkb - 1 && stid == 0) STC_STAMP(12);
-                    uint8_t *sp = base + (size_t)st * stage_bytes;
-                    const float4 *hiA = reinterpret_cast<const float4 *>(sp);
-                    float4 *loA = reinterpret_cast<float4 *>(sp + STC_A_BYTES);
-                    const float4 *hiB = reinterpret_cast<const float4 *>(sp + 2 * STC_A_BYTES);
-                    float4 *loB = reinterpret_cast<float4 *>(sp + 2 * STC_A_BYTES + B_BYTES);
-                    auto lo4 = [](float4 v) {
-                        float4 r;
-                        r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                        r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                        r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                        r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                        return r;
-                    };
-#pragma unroll
-                    for (int q = 0; q < (int)(STC_A_BYTES / 16 / 128); ++q) loA[stid + q * 128] = lo4(hiA[stid + q * 128]);
-                    const int nb4 = (int)(B_BYTES / 16);
-                    for (int q = stid; q < nb4; q += 128) loB[q] = lo4(hiB[q]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(stc_smem_u32(&ready[st])) : "memory");
-                }
             }
-            it += (uint32_t)nkb;
+            gM = g1;
             __syncwarp();
             // -------------------------------------------------------- partial product: tensor memory -> shared
             stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
             stc_fence_after();
             if (tid == 64) STC_STAMP(5);
+            if (warp == 0 && lane == 0 && a.partial_own && s + 1 < T) {
+                // every MMA of this step is complete, so every ring slot is free: request the first W tiles of the NEXT
+                // step now -- they travel while this CTA reduces, stores and waits at the counter barrier
+                const uint32_t gend = g1 + (uint32_t)((nkb < STAGES) ? nkb : STAGES);
+                for (uint32_t g = g1; g < gend; ++g) issue_W(g);
+                gW = gend;
+            }
             {
                 const int q = warp & 3, half = warp >> 2;
                 const int cbeg = half * (Npad / 2), cend = cbeg + Npad / 2;
@@ -326,6 +332,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             if (tid == 64) STC_STAMP(7);
         }
         // ------------------------------------------------------------ split-K reduction over DSMEM + epilogue
+        float *ring_s = ring + (size_t)(s & 1) * B * H;
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
             const int c = warp + 8 * ci;
@@ -354,6 +361,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
                 if (t >= Tb[ci]) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4 *>(out + ((int64_t)t * B + b) * H + j4) = v;
+                if (s + 1 < T) {      // the low half the tensor cores cannot see in v: next step's second B operand
+                    float4 lo;
+                    lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                    lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                    lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                    lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                    *reinterpret_cast<float4 *>(ring_s + (int64_t)b * H + j4) = lo;
+                }
             }
         }
         // ------------------------------------------------------------ publish S_t: one counter arrival per CTA
@@ -363,12 +378,12 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             if (tid == 0) {
                 STC_STAMP(9);
                 asm volatile("fence.proxy.async;" ::: "memory");
-                __threadfence();
-                atomicAdd(ctr, 1u);
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
                 STC_STAMP(10);
             }
         }
     }
+    (void)gM;
     // no CTA may exit while a peer can still read its shared memory
     stc_fence_before();
     stc_cluster_sync();
@@ -378,13 +393,29 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     }
 }
 
-// W^T (row-major H x H) for the BPTT A operand
-__global__ void stc_transpose_kernel(const float *__restrict__ w, float *__restrict__ wt, int H) {
+// Operand preparation, once per launch: out[0] = W (or W^T for BPTT), out[1] = its low half x - tf32(x); both H x H
+// row-major, stacked so that ONE 3-D TMA box fetches the hi and the lo tile of a k-block.
+__global__ void stc_prep_kernel(const float *__restrict__ w, float *__restrict__ stack, int H, int transpose) {
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
-    for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = w[(int64_t)(r0 + i) * H + c0 + threadIdx.x];
-    __syncthreads();
-    for (int i = threadIdx.y; i < 32; i += 8) wt[(int64_t)(c0 + i) * H + r0 + threadIdx.x] = tile[threadIdx.x][i];
+    float *hi = stack, *lo = stack + (size_t)H * H;
+    if (transpose) {
+        for (int i = threadIdx.y; i < 32; i += 8) tile[i][threadIdx.x] = w[(int64_t)(r0 + i) * H + c0 + threadIdx.x];
+        __syncthreads();
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const float v = tile[threadIdx.x][i];
+            const int64_t o = (int64_t)(c0 + i) * H + r0 + threadIdx.x;
+            hi[o] = v;
+            lo[o] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        }
+    } else {
+        for (int i = threadIdx.y; i < 32; i += 8) {
+            const int64_t o = (int64_t)(r0 + i) * H + c0 + threadIdx.x;
+            const float v = w[o];
+            hi[o] = v;
+            lo[o] = v - __uint_as_float(__float_as_uint(v) & 0xffffe000u);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------- host side
@@ -406,7 +437,7 @@ static StcEncodeFn stc_encode() {
     return fn;
 }
 
-struct StcPlan { int NS, Npad, stages, tmem_cols; uint32_t stage_bytes; size_t smem; };
+struct StcPlan { int NS, Npad, stages, tmem_cols, partial_own; uint32_t stage_bytes; size_t smem; };
 
 static int stc_max_clusters(size_t smem) {
     static int cached = -1;
@@ -430,7 +461,7 @@ static int stc_max_clusters(size_t smem) {
     return cached;
 }
 
-static constexpr size_t STC_SMEM_MAX = 200 * 1024;      // operand ring budget (+ barriers) within the 227 KB per CTA
+static constexpr size_t STC_SMEM_MAX = 208 * 1024;      // ring + partial budget (+ barriers) within the 227 KB per CTA
 
 static bool stc_plan(int H, int B, int ndir, StcPlan *p) {
     if (H % 128 != 0 || H < 512 || B < 1) return false;
@@ -449,14 +480,19 @@ static bool stc_plan(int H, int B, int ndir, StcPlan *p) {
     NS = (B + Npad - 1) / Npad;              // drop splits that would be empty
     p->NS = NS; p->Npad = Npad;
     p->stage_bytes = 2 * STC_A_BYTES + 2 * (uint32_t)Npad * 128u;
-    int stages = (int)(STC_SMEM_MAX / p->stage_bytes);
+    const size_t partial_bytes = (size_t)Npad * 512;
+    static int pf_env = -1;   // CTCB_SWEEP_TC_PREFETCH=0: never give the partial its own region (no W prefetch across steps)
+    if (pf_env < 0) { const char *e = getenv("CTCB_SWEEP_TC_PREFETCH"); pf_env = e ? atoi(e) : 1; }
+    // own region for the partial when at least two ring stages still fit beside it
+    p->partial_own = (pf_env && STC_SMEM_MAX >= partial_bytes + 2 * (size_t)p->stage_bytes) ? 1 : 0;
+    int stages = (int)((STC_SMEM_MAX - (p->partial_own ? partial_bytes : 0)) / p->stage_bytes);
     if (stages > 6) stages = 6;
     if (stages < 2) return false;
     p->stages = stages;
     int cols = 32;
     while (cols < Npad) cols <<= 1;
     p->tmem_cols = cols;
-    p->smem = (size_t)stages * p->stage_bytes + 512 + 1024;
+    p->smem = (size_t)stages * p->stage_bytes + (p->partial_own ? partial_bytes : 0) + 512 + 1024;
     return true;
 }
 
@@ -467,7 +503,12 @@ static bool stc_enabled(int H) {
     return H >= 1024 || (mode == 2 && H >= 512);
 }
 
-size_t sweep_tc_workspace_bytes(int H) { return (size_t)2 * H * H * sizeof(float) + 4096 + STC_TRACE_STEPS * 16 * 8; }
+// scratch: (hi, lo) stacks of both recurrent matrices, the rings of state low halves, the optional trace
+static size_t stc_ws_stack_bytes(int H) { return align_up((size_t)4 * H * H * sizeof(float), 1024); }
+static size_t stc_ws_ring_bytes(int H, int B) { return align_up((size_t)4 * B * H * sizeof(float), 1024); }
+size_t sweep_tc_workspace_bytes(int H, int B) {
+    return stc_ws_stack_bytes(H) + stc_ws_ring_bytes(H, B) + STC_TRACE_STEPS * 16 * 8 + 1024;
+}
 
 int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float *pre, const float *Wf, const float *Wb,
                  float *outF, float *outB, const float *actF, const float *actB, float maxAct, unsigned int *counters,
@@ -476,27 +517,25 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     const int ndir = Wb ? 2 : 1;
     StcPlan p;
     if (!stc_enabled(H) || !stc_plan(H, B, ndir, &p)) return CTCB_OK;
-    if (mode == 1 && (!ws || ws_bytes < sweep_tc_workspace_bytes(H))) return CTCB_OK;    // no room for W^T: other kernels
+    if (!ws || ws_bytes < sweep_tc_workspace_bytes(H, B) || (((uintptr_t)ws) & 255)) return CTCB_OK;   // no scratch: other kernels
     StcEncodeFn enc = stc_encode();
-    const float *A[2] = {Wf, Wb ? Wb : Wf};
-    if (mode == 1) {
-        float *wt = (float *)ws;
-        for (int d = 0; d < ndir; ++d) {
-            stc_transpose_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(A[d], wt + (size_t)d * H * H, H);
-            CTCB_LAUNCH_CHECK();
-            A[d] = wt + (size_t)d * H * H;
-        }
-        if (ndir == 1) A[1] = A[0];
+    float *stack = (float *)ws;
+    float *ring = (float *)((char *)ws + stc_ws_stack_bytes(H));
+    const float *Wd[2] = {Wf, Wb ? Wb : Wf};
+    for (int d = 0; d < ndir; ++d) {
+        stc_prep_kernel<<<dim3(H / 32, H / 32), dim3(32, 8), 0, st>>>(Wd[d], stack + (size_t)d * 2 * H * H, H, mode == 1 ? 1 : 0);
+        CTCB_LAUNCH_CHECK();
     }
     float *outs[2] = {outF, Wb ? outB : outF};
-    CUtensorMap tmW[2], tmS[2];
+    CUtensorMap tmW[2], tmS[2], tmL[2];
     for (int d = 0; d < 2; ++d) {
+        const int dd = (d < ndir) ? d : 0;
         {
-            cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)H};
-            cuuint64_t strides[1] = {(cuuint64_t)H * sizeof(float)};
-            cuuint32_t box[2] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM};
-            cuuint32_t es[2] = {1, 1};
-            CUresult r = enc(&tmW[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)A[d], dims, strides, box, es,
+            cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, 2};
+            cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)H * H * sizeof(float)};
+            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM, 2};
+            cuuint32_t es[3] = {1, 1, 1};
+            CUresult r = enc(&tmW[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)(stack + (size_t)dd * 2 * H * H), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(W) failed (%d)", (int)r);
@@ -506,24 +545,29 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
             cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)B * H * sizeof(float)};
             cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)p.Npad, 1};
             cuuint32_t es[3] = {1, 1, 1};
-            CUresult r = enc(&tmS[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)outs[d], dims, strides, box, es,
+            CUresult r = enc(&tmS[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)outs[dd], dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state) failed (%d)", (int)r);
+            dims[2] = 2;
+            r = enc(&tmL[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)(ring + (size_t)dd * 2 * B * H), dims, strides, box, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state lo) failed (%d)", (int)r);
         }
     }
     SweepTcArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.out[0] = outs[0]; a.out[1] = outs[1]; a.act[0] = actF; a.act[1] = Wb ? actB : actF; a.maxAct = maxAct;
+    a.ring[0] = ring; a.ring[1] = ring + (size_t)(ndir - 1) * 2 * B * H;
     a.err = counters; a.counters = counters + 16;
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
-    a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols;
+    a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
     a.trace = nullptr;
     {
         static int trace_env = -1;
         if (trace_env < 0) trace_env = getenv("CTCB_SWEEP_TRACE") ? 1 : 0;
-        if (trace_env && ws && ws_bytes >= sweep_tc_workspace_bytes(H))
-            a.trace = (unsigned long long *)((char *)ws + (size_t)2 * H * H * sizeof(float) + 4096);
+        if (trace_env) a.trace = (unsigned long long *)((char *)ws + stc_ws_stack_bytes(H) + stc_ws_ring_bytes(H, B));
     }
     CTCB_CUDA_CHECK(cudaMemsetAsync(a.counters, 0, sizeof(unsigned int) * (size_t)(ndir * p.NS), st));
     CTCB_CUDA_CHECK(cudaFuncSetAttribute(sweep_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem));
@@ -541,7 +585,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     static int coop = -1;     // does this driver accept cluster + cooperative together?
     if (coop != 0) {
         cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], tmL[0], tmL[1], a);
         if (e == cudaSuccess) { coop = 1; count_launch(); *handled = true; return CTCB_OK; }
         cudaGetLastError();
         if (coop == 1) return set_error(CTCB_ECUDA, "sweep_tc: launch failed: %s", cudaGetErrorString(e));
@@ -549,7 +593,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
         if (getenv("CTCB_DEBUG")) fprintf(stderr, "[ctcb] tensor-core sweep: cooperative+cluster launch refused (%s), plain cluster launch\n", cudaGetErrorString(e));
     }
     cfg.numAttrs = 1;         // grid <= one wave of clusters by construction (stc_plan)
-    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], a));
+    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], tmL[0], tmL[1], a));
     count_launch();
     *handled = true;
     return CTCB_OK;

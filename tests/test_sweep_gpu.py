@@ -61,7 +61,7 @@ def test_sweep_forward_and_bptt(H, B, T, cuda):
     d_pre, d_Wf, d_Wb = dev(pre), dev(Wf), dev(Wb)
     d_len = torch.from_numpy(lens.astype(np.int32)).cuda()
     oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty(T, B, H, device="cuda")
-    nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
+    nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H, B))
     scratch = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
     check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(d_len), ptr(d_pre), ptr(d_Wf), ptr(d_Wb), ptr(oF), ptr(oB), None,
                                   None, maxAct, ptr(scratch), nscr, _ctcb.current_stream()))

@@ -17,7 +17,7 @@ for t in range(T):
     F[t] = np.clip(p64[t] + (F[t - 1] @ W64.T if t > 0 else 0.0), 0.0, 20.0)
 dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
 oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty_like(oF)
-nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
+nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H, B))
 scr = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
 d_lens, d_pre, d_Wf, d_Wb = dev(lens), dev(pre), dev(Wf), dev(Wb)       # keep the device copies alive
 check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(d_lens), ptr(d_pre), ptr(d_Wf), ptr(d_Wb), ptr(oF), ptr(oB), None, None,

@@ -13,7 +13,7 @@ Wb = (torch.rand(H, H, device="cuda", generator=g) * 2 - 1) * s
 pre = torch.randn(T, B, H, device="cuda", generator=g)
 lens = torch.full((B,), T, dtype=torch.int32, device="cuda")
 oF = torch.empty(T, B, H, device="cuda"); oB = torch.empty_like(oF); dF = torch.empty_like(oF); dB = torch.empty_like(oF)
-nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H))
+nscr = int(lib.ctcb_brnn_sweep_workspace_bytes(H, B))
 scr = torch.zeros(nscr // 4, dtype=torch.int32, device="cuda")
 st = _ctcb.current_stream()
 def fwd(): check(lib.ctcb_brnn_sweep_f32(0, T, B, H, ptr(lens), ptr(pre), ptr(Wf), ptr(Wb), ptr(oF), ptr(oB), None, None, 20.0, ptr(scr), nscr, st))
@@ -30,7 +30,8 @@ for name, fn in (("fwd", fwd), ("bptt", bwd)):
         e0.elapsed_time(e1) / 20, 1e3 * e0.elapsed_time(e1) / 20 / T, int(scr[0])))
 
 if os.environ.get("CTCB_SWEEP_TRACE"):
-    off = (4096 + 2 * H * H * 4 + 4096) // 8
+    al = lambda x: (x + 1023) // 1024 * 1024
+    off = (4096 + al(4 * H * H * 4) + al(4 * B * H * 4)) // 8
     tr = scr.view(torch.int64)[off:off + 64 * 16].cpu().numpy().reshape(64, 16)
     names = ["step top", "counter seen", "TMA issued", "first ready (MMA)", "done commit issued", "done seen (epi)",
              "partial in smem", "after cluster sync", "after finalize stores", "after syncthreads", "after arrive",
