@@ -31,6 +31,11 @@ namespace ctcb {
 
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;   // 32 fp32 = 128 bytes = one swizzle span
+// Measured (tools/micro/umma_rate.cu + the per-phase trace of the recurrent sweep): a kind::tf32 MMA costs max(45, N/2)
+// cycles, i.e. 12 x 128 = 1536 cycles per k-block at BN = 256, while ONE warpgroup of splitters needed ~3000: the tensor
+// pipe sat at 25-50 %.  Two warpgroups, loads hoisted above the stores, bring the split under the MMA time.
+constexpr int TC_SPLIT_WARPS = 8;
+constexpr int TC_THREADS = 128 + 32 * TC_SPLIT_WARPS;
 
 struct GemmTcArgs {
     int M, N, K;
@@ -112,7 +117,7 @@ __device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int
 }
 
 template <int BN, int STAGES>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TC_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
     constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
     constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
@@ -135,7 +140,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int s = 0; s < STAGES; ++s) {
             tc_mbar_init(tc_smem_u32(&bars[s]), 1);
             tc_mbar_init(tc_smem_u32(&bars[STAGES + s]), 1);
-            tc_mbar_init(tc_smem_u32(&ready[s]), 4);          // one arrival per splitter warp
+            tc_mbar_init(tc_smem_u32(&ready[s]), TC_SPLIT_WARPS);   // one arrival per splitter warp
         }
         tc_mbar_init(tc_smem_u32(&bars[2 * STAGES]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -187,27 +192,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             tc_commit(tc_smem_u32(&bars[2 * STAGES]));             // accumulator complete
         } else if (warp >= 4) {
-            // ------------------------------------------------------------ splitter (128 threads)
+            // ------------------------------------------------------------ splitters (TC_SPLIT_WARPS warps)
+            constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
+            constexpr int NA = (int)(A_BYTES / 16) / NSPLIT, NB = (int)(B_BYTES / 16) / NSPLIT;
+            static_assert(NA * NSPLIT * 16 == (int)A_BYTES && NB * NSPLIT * 16 == (int)B_BYTES, "tile not divisible over the splitters");
             const int tid = threadIdx.x - 128;
+            auto lo4 = [](float4 v) {
+                float4 r;
+                r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+                r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+                r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+                r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+                return r;
+            };
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
-                float4 *hiA = reinterpret_cast<float4 *>(base + s * STAGE_BYTES);
+                const float4 *hiA = reinterpret_cast<const float4 *>(base + s * STAGE_BYTES);
                 float4 *loA = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + A_BYTES);
-                float4 *hiB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES);
+                const float4 *hiB = reinterpret_cast<const float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES);
                 float4 *loB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES);
-                auto lo4 = [](float4 v) {
-                    float4 r;
-                    r.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-                    r.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-                    r.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-                    r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    return r;
-                };
+                float4 va[NA], vb[NB];       // every load first, then every store: the two never alias
 #pragma unroll
-                for (int q = 0; q < (int)(A_BYTES / 16 / 128); ++q) loA[tid + q * 128] = lo4(hiA[tid + q * 128]);
+                for (int q = 0; q < NA; ++q) va[q] = hiA[tid + q * NSPLIT];
 #pragma unroll
-                for (int q = 0; q < (int)(B_BYTES / 16 / 128); ++q) loB[tid + q * 128] = lo4(hiB[tid + q * 128]);
+                for (int q = 0; q < NB; ++q) vb[q] = hiB[tid + q * NSPLIT];
+#pragma unroll
+                for (int q = 0; q < NA; ++q) loA[tid + q * NSPLIT] = lo4(va[q]);
+#pragma unroll
+                for (int q = 0; q < NB; ++q) loB[tid + q * NSPLIT] = lo4(vb[q]);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> tensor-core (async) proxy
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&ready[s])) : "memory");
@@ -398,7 +411,7 @@ static int launch_tc(const CUtensorMap &tA, const CUtensorMap &tB, const GemmTcA
     constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (3 * STAGES + 1) * 8 + 16 + 1024;
     CTCB_CUDA_CHECK(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, splits);
-    gemm_tc_kernel<BN, STAGES><<<grid, 256, smem, st>>>(tA, tB, g);
+    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(tA, tB, g);
     CTCB_LAUNCH_CHECK();
     return CTCB_OK;
 }
