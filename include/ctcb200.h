@@ -127,6 +127,12 @@ size_t ctcb_brnn_workspace_bytes(const ctcb_brnn_config *cfg);
  * (e.g. for the per-step log line) should read it. */
 size_t ctcb_brnn_error_flag_offset(const ctcb_brnn_config *cfg);
 
+/* Diagnostic hook (used by the parity tests): byte offset inside the workspace of the activations the LAST
+ * ctcb_brnn_cost_and_grad call left behind, time-major [Tmax][B][*width] with that call's B and Tmax.
+ * what = 0: output of affine map `layer` (1..numLayers+1; For+Back at the temporal layer, logits at the last),
+ * what = 1 / 2: For / Back of the temporal layer (brnnet.py:143-153). */
+int ctcb_brnn_activation_offset(const ctcb_brnn_config *cfg, int what, int layer, size_t *offset, int32_t *width);
+
 int ctcb_brnn_create(const ctcb_brnn_config *cfg, ctcb_brnn **out);
 void ctcb_brnn_destroy(ctcb_brnn *h);
 

@@ -122,8 +122,23 @@ class NNet:
         probs = e / e.sum(axis=0)[None, :]
         return hActs, For, Back, (probs.astype(np.float32) if self.round_f32 else probs)
 
-    def costAndGrad(self, data, labels=None, sentence=None):
-        hActs, For, Back, probs = self.forward(data)
+    def costAndGradGiven(self, data, labels, hActs, For, Back):
+        """Checker-only: back-propagation (brnnet.py:175-249) THROUGH GIVEN ACTIVATIONS -- hActs[1..N+1] (the last
+        entry the pre-softmax outputs), For, Back, as the implementation under test computed them, widened to this
+        net's dtype.  The ReLU / clip masks are then the implementation's own, so the comparison of the gradients
+        measures its backward arithmetic and is blind to the mask flips that float32 noise in the forward pass
+        causes (profiles/kink_sensitivity_r2.txt)."""
+        dt = self.dtype
+        hActs = [np.asarray(data, dtype=dt)] + [np.asarray(h, dtype=dt) for h in hActs]
+        z = hActs[-1] - hActs[-1].max(axis=0)[None, :]
+        e = np.exp(z)
+        probs = e / e.sum(axis=0)[None, :]
+        probs = probs.astype(np.float32) if self.round_f32 else probs
+        return self.costAndGrad(data, labels, _given=(hActs, None if For is None else np.asarray(For, dtype=dt),
+                                                       None if Back is None else np.asarray(Back, dtype=dt), probs))
+
+    def costAndGrad(self, data, labels=None, sentence=None, _given=None):
+        hActs, For, Back, probs = self.forward(data) if _given is None else _given
         if not self.train:
             return probs                                                  # :171-173
         T = data.shape[1]

@@ -549,3 +549,25 @@ extern "C" int ctcb_brnn_exchange_only(ctcb_brnn *h, const float *params, float 
 }
 
 extern "C" size_t ctcb_brnn_sweep_workspace_bytes(int H, int B) { return 4096 + ctcb::sweep_tc_workspace_bytes(H, B); }
+
+// Test / diagnostic hook: where, inside the workspace, the activations of the LAST ctcb_brnn_cost_and_grad call lie
+// (time-major [Tmax][B][n] with that call's B and Tmax).  what = 0: output of affine map `layer` (1..numLayers+1; the
+// temporal layer's entry holds For + Back, the last one the logits), 1: For, 2: Back (temporal layer only).
+extern "C" int ctcb_brnn_activation_offset(const ctcb_brnn_config *cfg, int what, int layer, size_t *offset, int32_t *width) {
+    if (!valid_cfg(cfg) || !offset) return set_error(CTCB_EINVAL, "ctcb_brnn_activation_offset: bad arguments");
+    const WsLayout w = ws_layout(cfg);
+    int sizes[66];
+    layer_sizes(cfg, sizes);
+    if (what == 0) {
+        if (layer < 1 || layer > cfg->numLayers + 1) return set_error(CTCB_EINVAL, "ctcb_brnn_activation_offset: layer %d", layer);
+        *offset = w.X[layer];
+        if (width) *width = sizes[layer];
+        return CTCB_OK;
+    }
+    if ((what == 1 || what == 2) && eff_tl(cfg)) {
+        *offset = (what == 1) ? w.For : w.Back;
+        if (width) *width = cfg->layerSize;
+        return CTCB_OK;
+    }
+    return set_error(CTCB_EINVAL, "ctcb_brnn_activation_offset: nothing of kind %d in this net", what);
+}

@@ -7,16 +7,22 @@ rnnetcpu.py) on the same seeded inputs:
   C4 at B=2                   numLayers=5, temporalLayer=3, H=2048,       T=1500, D=41, K=35, |l|=150
                               (reference defaults runNNet.py:34-38, swbd-utils/runSwbd.sh:6-22)
 
-Tolerances (north_star: 1e-4 relative on loss and gradient).  Per-utterance cost: 1e-4 relative, every config.
-Gradient, per tensor: ||g - g_ref||_F / ||g_ref||_F <= 1e-4 at C2.  At the C3 / C4 sizes the gradient of THIS function
-is not 1e-4-continuous in float32: the net has 6-25 million ReLU / clip units per layer, a float32-roundoff-sized
-change of a pre-activation flips the mask (brnnet.py:155-157,208-209) of the few units that sit within 1e-6 of a kink,
-and every flip moves one row of the weight gradients by a full term -- the float64 oracle run against ITSELF with 1e-6
-relative input noise changes dW1 by 2.9e-4 and with 1e-5 by 2.1e-3 (profiles/kink_sensitivity_r2.txt,
-tools/kink_sensitivity.py), while a float32 NumPy run of the same net that happens to flip nothing agrees to 3e-7.  No
-float32 implementation, the reference's cudamat one included, can meet a Frobenius bound of 1e-4 there.  So at those
-sizes the test asserts (a) the MEDIAN over rows of the row-wise relative error <= 1e-4 (rows without a flipped unit: the
-arithmetic itself), (b) the Frobenius error <= 5e-3 (the flips stay a handful), and records both.
+Tolerances (north_star: 1e-4 relative on loss and gradient):
+  * per-utterance cost <= 1e-4 relative, every config;
+  * forward pass: every activation array (each layer's output, For, Back, logits) within 1e-4 of the oracle's, relative to
+    that array's largest magnitude;
+  * backward pass: every gradient tensor within 1e-4 (relative Frobenius) of the oracle's back-propagation THROUGH THE
+    GPU'S OWN ACTIVATIONS (oracle.costAndGradGiven; the activations are read back through
+    ctcb_brnn_activation_offset).  Together with the forward bound this is parity of the whole function, stated so that
+    it is meaningful: the gradient of this net is not 1e-4-continuous in float32.  It has 6-25 million ReLU / clip units
+    per layer; a float32-roundoff-sized change of a pre-activation flips the mask (brnnet.py:155-157,208-209) of the few
+    units that sit within ~1e-6 of a kink, and each flip changes the deltas below it by a full term -- the float64 oracle
+    run against ITSELF with 1e-6 relative input noise moves dW1 by 2.9e-4, with 1e-5 by 2.1e-3
+    (profiles/kink_sensitivity_r2.txt, tools/kink_sensitivity.py), while a float32 NumPy run that happens to flip
+    nothing agrees to 3e-7.  No float32 implementation, the reference's cudamat one included, can meet 1e-4 against
+    float64 masks at these sizes;
+  * the plain comparison (oracle with its own float64 masks) is still made: <= 1e-4 at C2, recorded and bounded by 5e-3
+    at the larger configs.
 The measured errors are written to gpurun_out/parity_configs.json."""
 import json
 import os
@@ -42,20 +48,6 @@ CASES = {
 
 def _rel(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
-
-
-def _row_median(a, b):
-    """Median over rows of ||a_i - b_i|| / ||b_i||: insensitive to the few rows a flipped ReLU mask touches."""
-    a2, b2 = a.reshape(a.shape[0], -1), b.reshape(b.shape[0], -1)
-    if a2.shape[1] == 1:                      # a bias: one row per unit would be a single number each -> use blocks of 16
-        n = a2.shape[0] // 16 * 16
-        if n >= 64:
-            a2, b2 = a2[:n].reshape(-1, 16), b2[:n].reshape(-1, 16)
-        else:
-            a2, b2 = a2.reshape(1, -1), b2.reshape(1, -1)
-    num = np.linalg.norm(a2 - b2, axis=1)
-    den = np.maximum(np.linalg.norm(b2, axis=1), 1e-30)
-    return float(np.median(num / den))
 
 
 def _record(name, rec):
@@ -88,27 +80,65 @@ def test_full_net_at_baseline_config(name, cuda):
     nn.initParams()
     costs, grad, skips = nn.costAndGradBatch(datas, labelss)
     g_host = [(dw.cpu().numpy().astype(np.float64), db.cpu().numpy().astype(np.float64)) for dw, db in grad]
+
+    # the activations the GPU pass left in its workspace, time-major [Tmax][B][n]
+    import ctypes
+    from _ctcb import lib, check
+    Tmax = max(lens)
+
+    def act(what, layer):
+        off, width = ctypes.c_size_t(), ctypes.c_int32()
+        check(lib.ctcb_brnn_activation_offset(ctypes.byref(nn._cfg), what, layer, ctypes.byref(off), ctypes.byref(width)))
+        n = Tmax * B * width.value
+        return nn._ws[off.value:off.value + 4 * n].view(cuda.float32).view(Tmax, B, width.value).cpu().numpy()
+
+    X = [None] + [act(0, i) for i in range(1, N + 2)]
+    For, Back = act(1, 0), act(2, 0)
     del nn
     cuda.cuda.empty_cache()
-    o_costs, o_grad, o_skips = on.costAndGradBatch(datas, labelss)
+
+    o_costs, o_grad, o_skips = on.costAndGradBatch(datas, labelss)          # the oracle on its own (float64 masks)
     assert np.array_equal(skips, o_skips) and not skips.any()
     cost_err = float(np.max(np.abs(costs - o_costs) / np.abs(o_costs)))
-    errs, meds = [], []
+    plain = []
     for i, ((dw, db), (odw, odb)) in enumerate(zip(g_host, o_grad)):
-        errs.append(_rel(dw, odw))
-        meds.append(_row_median(dw, odw))
+        plain.append(_rel(dw, odw))
         if i <= N:
-            errs.append(_rel(db.reshape(-1), odb.reshape(-1)))
-            meds.append(_row_median(db.reshape(-1, 1), odb.reshape(-1, 1)))
+            plain.append(_rel(db.reshape(-1), odb.reshape(-1)))
+
+    # forward parity, pointwise, and the oracle's back-propagation through the GPU's activations
+    fwd_err = 0.0
+    tot = [[np.zeros_like(w), np.zeros_like(b)] for w, b in on.stack]
+    for u, (d, l) in enumerate(zip(datas, labelss)):
+        Tu = lens[u]
+        h, F, Bk, _ = on.forward(d)
+        for i in range(1, N + 2):
+            g = X[i][:Tu, u, :].T.astype(np.float64)
+            fwd_err = max(fwd_err, float(np.abs(g - h[i]).max() / max(np.abs(h[i]).max(), 1e-30)))
+        gF, gB = For[:Tu, u, :].T.astype(np.float64), Back[:Tu, u, :].T.astype(np.float64)
+        fwd_err = max(fwd_err, float(np.abs(gF - F).max() / np.abs(F).max()), float(np.abs(gB - Bk).max() / np.abs(Bk).max()))
+        c_, g_, s_ = on.costAndGradGiven(d, l, [X[i][:Tu, u, :].T for i in range(1, N + 2)], gF, gB)
+        assert not s_
+        for (tw, tb), (gw, gb) in zip(tot, g_):
+            tw += gw
+            tb += gb
+    given = []
+    for i, ((dw, db), (odw, odb)) in enumerate(zip(g_host, tot)):
+        given.append(_rel(dw, odw))
+        if i <= N:
+            given.append(_rel(db.reshape(-1), odb.reshape(-1)))
+
     small = (name == "c2_as_benchmarked")
-    frob_tol = GRAD_TOL if small else 5e-3
-    _record(name, dict(config=c, cost_rel_err_max=cost_err, grad_frobenius_rel_err_max=max(errs),
-                       grad_frobenius_rel_err_per_tensor=errs, grad_row_median_rel_err_max=max(meds),
-                       grad_row_median_rel_err_per_tensor=meds,
-                       tolerance=dict(cost=COST_TOL, grad_row_median=GRAD_TOL, grad_frobenius=frob_tol)))
+    plain_tol = GRAD_TOL if small else 5e-3
+    _record(name, dict(config=c, cost_rel_err_max=cost_err, forward_activation_rel_err_max=fwd_err,
+                       grad_rel_err_given_gpu_activations_max=max(given), grad_rel_err_given_gpu_activations=given,
+                       grad_rel_err_vs_float64_masks_max=max(plain), grad_rel_err_vs_float64_masks=plain,
+                       tolerance=dict(cost=COST_TOL, forward=1e-4, grad_given_activations=GRAD_TOL,
+                                      grad_vs_float64_masks=plain_tol)))
     assert cost_err <= COST_TOL, cost_err
-    assert max(meds) <= GRAD_TOL, meds
-    assert max(errs) <= frob_tol, errs
+    assert fwd_err <= 1e-4, fwd_err
+    assert max(given) <= GRAD_TOL, given
+    assert max(plain) <= plain_tol, plain
 
 
 def test_two_shards_summed_equal_the_full_batch_with_l2(cuda):
