@@ -178,6 +178,6 @@ def test_two_shards_summed_equal_the_full_batch_with_l2(cuda):
     a, b = total.cpu().numpy().astype(np.float64), g_full.cpu().numpy().astype(np.float64)
     assert _rel(a[:-4], b[:-4]) < 2e-6
     assert a[-4] == b[-4] == 7 and abs(a[-3] - b[-3]) / abs(b[-3]) < 1e-6 and a[-2] == b[-2] == 0 and a[-1] == b[-1] == 0
-    # and the naive per-rank L2 would NOT have matched: the deferred sum differs from it by exactly reg*W
+    # a per-rank L2 term would have added reg*W twice: that difference is far above the tolerance used above
     w = full.params.cpu().numpy().astype(np.float64)
-    assert np.linalg.norm(reg * w) > 1e-3 * np.linalg.norm(b[:-4])
+    assert np.linalg.norm(reg * w) > 100 * 2e-6 * np.linalg.norm(b[:-4])
