@@ -45,6 +45,7 @@ struct GemmTcArgs {
     float *partial;      // split-K partials [splits][M][N] or nullptr
     int kb_per_split;    // k-blocks per gridDim.z slice
     int nmma;            // debug (CTCB_GEMM_MMAS): 3 = full 3xTF32, 1 = hi.hi only (plain TF32, for rate experiments)
+    int a_mn, b_mn;      // operand is MN-major in memory (stored K x M / K x N): fed to the tensor cores as it lies
 };
 
 // ---------------------------------------------------------------------------------- PTX wrappers
@@ -101,10 +102,25 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
+// MN-major operand (the M / N index is the contiguous one in memory), SWIZZLE_128B.  Canonical layout in 16-byte units
+// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -- 32 floats of M
+// contiguous, 8 k-rows 128 bytes apart (one 1 KB swizzle atom = one K = 8 MMA), further groups of 32 M at LBO.  A TMA
+// box of {32 m, 32 k} floats with 128B swizzle is exactly four such atoms (k-steps) 1024 bytes apart, and the boxes of
+// a tile are laid 4096 bytes apart: LBO = 4096, SBO = 1024.
+__device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
+    d |= (uint64_t)(4096 >> 4) << 16;        // LBO: next group of 32 along M / N
+    d |= (uint64_t)(1024 >> 4) << 32;        // SBO: next group of 8 along K
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
 // Instruction descriptor for kind::tf32 (InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
-// both K-major, N>>3 at [17,23), M>>4 at [24,29).
-__host__ __device__ constexpr uint32_t tc_idesc(int m, int n) {
-    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// a_major [15] / b_major [16] (0 = K-major, 1 = MN-major), N>>3 at [17,23), M>>4 at [24,29).
+__host__ __device__ constexpr uint32_t tc_idesc(int m, int n, int a_mn = 0, int b_mn = 0) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a_mn & 1) << 15) | ((uint32_t)(b_mn & 1) << 16) |
+           ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int m, int n) {
@@ -164,28 +180,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_mbar_expect_tx(full, A_BYTES + B_BYTES);
                 uint8_t *st = base + s * STAGE_BYTES;
                 const int k = (kb0 + i) * TC_BK;
-                tc_tma_load_2d(tc_smem_u32(st), &tmA, full, k, m0);
-                tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES), &tmB, full, k, n0);
+                if (g.a_mn) {      // four boxes of {32 m, 32 k}
+#pragma unroll
+                    for (int j = 0; j < TC_BM / 32; ++j) tc_tma_load_2d(tc_smem_u32(st + j * 4096), &tmA, full, m0 + 32 * j, k);
+                } else {
+                    tc_tma_load_2d(tc_smem_u32(st), &tmA, full, k, m0);
+                }
+                if (g.b_mn) {
+#pragma unroll
+                    for (int j = 0; j < BN / 32; ++j) tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES + j * 4096), &tmB, full, n0 + 32 * j, k);
+                } else {
+                    tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES), &tmB, full, k, n0);
+                }
             }
         } else if (warp == 1 && lane == 0) {
             // ------------------------------------------------------------ MMA issuer
-            constexpr uint32_t idesc = tc_idesc(TC_BM, BN);
+            const uint32_t idesc = tc_idesc(TC_BM, BN, g.a_mn, g.b_mn);
+            // per k-step (8 floats of K): 32 bytes along the swizzled row (K-major) or one whole 1 KB atom (MN-major)
+            const uint64_t stepA = (uint64_t)((g.a_mn ? 1024 : 32) >> 4), stepB = (uint64_t)((g.b_mn ? 1024 : 32) >> 4);
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&ready[s]), (uint32_t)(use & 1));      // hi landed and lo written
                 tc_fence_after();
                 const uint32_t a = tc_smem_u32(base + s * STAGE_BYTES);
-                const uint64_t dA = tc_smem_desc(a), dAl = tc_smem_desc(a + A_BYTES);
-                const uint64_t dB = tc_smem_desc(a + 2 * A_BYTES), dBl = tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
+                const uint64_t dA = g.a_mn ? tc_smem_desc_mn(a) : tc_smem_desc(a);
+                const uint64_t dAl = g.a_mn ? tc_smem_desc_mn(a + A_BYTES) : tc_smem_desc(a + A_BYTES);
+                const uint64_t dB = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES) : tc_smem_desc(a + 2 * A_BYTES);
+                const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES + B_BYTES) : tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
 #pragma unroll
                 for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-                    const uint64_t adv = (uint64_t)((k8 * 32) >> 4);   // 8 floats = 32 bytes along the swizzled row
+                    const uint64_t aa = (uint64_t)k8 * stepA, ab = (uint64_t)k8 * stepB;
                     if (g.nmma >= 3) {
-                        tc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                        tc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                              // hi . lo
-                        tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                               // hi . hi
+                        tc_mma_tf32(tmem_d, dAl + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                        tc_mma_tf32(tmem_d, dA + aa, dBl + ab, idesc, 1u);                              // hi . lo
+                        tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, 1u);                               // hi . hi
                     } else {
-                        tc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
+                        tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
                     }
                 }
                 tc_commit(tc_smem_u32(&bars[STAGES + s]));         // slot free once these MMAs have read it
@@ -357,6 +387,20 @@ static int make_map(CUtensorMap *m, const float *ptr, int rows, int K, int64_t l
     return CTCB_OK;
 }
 
+// MN-major operand: stored K x MN (MN contiguous, pitch ld elements); box = {32 along MN, 32 along K}, 128B swizzle
+static int make_map_mn(CUtensorMap *m, const float *ptr, int mn, int K, int64_t ld) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    cuuint64_t dims[2] = {(cuuint64_t)mn, (cuuint64_t)K};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    cuuint32_t box[2] = {32, (cuuint32_t)TC_BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled (MN-major) failed (%d) mn=%d K=%d ld=%lld", (int)r, mn, K, (long long)ld);
+    return CTCB_OK;
+}
+
 static inline int64_t pad4(int64_t x) { return (x + 3) / 4 * 4; }
 
 static int tc_pick_bn(int M, int N, int K) {
@@ -430,7 +474,14 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     // ---- operand A as M x K, K-major: stored M x K (transA=0) or K x M (transA=1)
     const float *Ause; int64_t lda_use;
     auto ew_grid = [](int64_t n) { int64_t b = (n + 255) / 256; const int cap = 16 * num_sms(); return (int)(b > cap ? cap : (b < 1 ? 1 : b)); };
-    if (transA) {
+    static int mn_env = -1;     // CTCB_GEMM_MN=0: always transpose into K-major copies (the round-1 path)
+    if (mn_env < 0) { const char *e = getenv("CTCB_GEMM_MN"); mn_env = e ? atoi(e) : 1; }
+    auto tma_ok = [](const float *p_, int64_t ld_) { return (ld_ % 4 == 0) && (((uintptr_t)p_) % 16 == 0); };
+    const int a_mn = (transA && mn_env && tma_ok(A, lda)) ? 1 : 0;
+    const int b_mn = (!transB && mn_env && tma_ok(B, ldb)) ? 1 : 0;
+    if (a_mn) {
+        Ause = A; lda_use = lda;                       // stored K x M: MN-major A, no copy
+    } else if (transA) {
         tc_split_transpose_kernel<<<dim3((M + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(A, lda, K, M, Ahi, nullptr, Kp);
         CTCB_LAUNCH_CHECK();
         Ause = Ahi; lda_use = Kp;
@@ -443,7 +494,9 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     }
     // ---- operand B as N x K, K-major: stored N x K (transB=1) or K x N (transB=0)
     const float *Buse; int64_t ldb_use;
-    if (!transB) {
+    if (b_mn) {
+        Buse = B; ldb_use = ldb;                       // stored K x N: MN-major B, no copy
+    } else if (!transB) {
         tc_split_transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(B, ldb, K, N, Bhi, nullptr, Kp);
         CTCB_LAUNCH_CHECK();
         Buse = Bhi; ldb_use = Kp;
@@ -459,6 +512,7 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     int splits = tc_choose_splits(M, N, K, BN);
     const int nkb = (K + TC_BK - 1) / TC_BK;
     GemmTcArgs g;
+    g.a_mn = a_mn; g.b_mn = b_mn;
     g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.bias = bias; g.relu = relu; g.mask = mask_src;
     {
         static int nmma_env = -1;
@@ -471,8 +525,8 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
 
     CUtensorMap tA, tB;
     int rc;
-    if ((rc = make_map(&tA, Ause, M, K, lda_use, TC_BM)) != CTCB_OK) return rc;
-    if ((rc = make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
+    if ((rc = a_mn ? make_map_mn(&tA, Ause, M, K, lda_use) : make_map(&tA, Ause, M, K, lda_use, TC_BM)) != CTCB_OK) return rc;
+    if ((rc = b_mn ? make_map_mn(&tB, Buse, N, K, ldb_use) : make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
     static int stages_env = -1;   // CTCB_GEMM_STAGES=2 with BN=64: 96 KB/CTA -> two CTAs per SM overlap prologue/epilogue
     if (stages_env < 0) { const char *e = getenv("CTCB_GEMM_STAGES"); stages_env = e ? atoi(e) : 0; }
     if (BN == 64 && stages_env == 2) rc = launch_tc<64, 2>(tA, tB, g, splits, st);
