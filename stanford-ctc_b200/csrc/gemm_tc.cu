@@ -102,18 +102,20 @@ __device__ __forceinline__ uint64_t tc_smem_desc(uint32_t smem_addr) {
     d |= (uint64_t)2 << 61;                  // SWIZZLE_128B
     return d;
 }
-// MN-major operand (the M / N index is the contiguous one in memory), SWIZZLE_128B.  Canonical layout in 16-byte units
-// (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>): ((8,n),(8,k)) : ((1,LBO),(8,SBO)) -- 32 floats of M
-// contiguous, 8 k-rows 128 bytes apart (one 1 KB swizzle atom = one K = 8 MMA), further groups of 32 M at LBO.  A TMA
-// box of {32 m, 32 k} floats with 128B swizzle is exactly four such atoms (k-steps) 1024 bytes apart, and the boxes of
-// a tile are laid 4096 bytes apart: LBO = 4096, SBO = 1024.
+// MN-major operand (the M / N index is the contiguous one in memory).  For 32-bit operands the tensor cores accept
+// exactly one swizzled MN-major layout, SWIZZLE_128B_BASE32B (layout type 1; every other type makes the MMA read zeros --
+// probed with tools/micro/umma_layout_probe.cu, which also gave the address map): rows of 128 bytes hold 32 consecutive
+// M (N) values of one k; 4 k-rows form a 512-byte atom in which the 32-byte chunks are XOR-ed with the row index
+// (Swizzle<2,5,2>); the next 4 k are SBO bytes further, the next 32 M (N) values LBO bytes.  TMA's
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B writes exactly this pattern, so a box of {32 m, 32 k} floats is four K = 8 MMA
+// steps 1024 bytes apart (SBO = 512 inside a step) and the boxes of a tile lie 4096 bytes apart (LBO).
 __device__ __forceinline__ uint64_t tc_smem_desc_mn(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3ffff) >> 4);
     d |= (uint64_t)(4096 >> 4) << 16;        // LBO: next group of 32 along M / N
-    d |= (uint64_t)(1024 >> 4) << 32;        // SBO: next group of 8 along K
+    d |= (uint64_t)(512 >> 4) << 32;         // SBO: next group of 4 along K
     d |= (uint64_t)1 << 46;
-    d |= (uint64_t)2 << 61;
+    d |= (uint64_t)1 << 61;                  // SWIZZLE_128B_BASE32B
     return d;
 }
 // Instruction descriptor for kind::tf32 (InstrDescriptor): D=F32 [4,6)=1, A=TF32 [7,10)=2, B=TF32 [10,13)=2,
@@ -387,7 +389,7 @@ static int make_map(CUtensorMap *m, const float *ptr, int rows, int K, int64_t l
     return CTCB_OK;
 }
 
-// MN-major operand: stored K x MN (MN contiguous, pitch ld elements); box = {32 along MN, 32 along K}, 128B swizzle
+// MN-major operand: stored K x MN (MN contiguous, pitch ld elements); box = {32 along MN, 32 along K}, 128B swizzle with 32-byte atoms
 static int make_map_mn(CUtensorMap *m, const float *ptr, int mn, int K, int64_t ld) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
@@ -396,7 +398,7 @@ static int make_map_mn(CUtensorMap *m, const float *ptr, int mn, int K, int64_t 
     cuuint32_t box[2] = {32, (cuuint32_t)TC_BK};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "cuTensorMapEncodeTiled (MN-major) failed (%d) mn=%d K=%d ld=%lld", (int)r, mn, K, (long long)ld);
     return CTCB_OK;
 }
@@ -417,15 +419,27 @@ static int tc_pick_bn(int M, int N, int K) {
     return 128;
 }
 
+// The tensor cores accumulate in fp32 with truncation, not rounding: measured (tools/gemm_check.py big), the relative
+// error of one accumulator chain grows linearly with its length -- 4e-6 at K = 512, 1.5e-5 at K = 2048, 3.4e-4 at
+// K = 48 000, 1.3e-3 at K = 192 000 (a weight gradient over T*B rows).  So no chain is allowed to be longer than
+// TC_CHAIN_KB k-blocks (K = 2048): longer contractions are split over K and the partial sums are added in fp32 with
+// round-to-nearest by the reduce kernel (deterministic order).
+constexpr int TC_CHAIN_KB = 64;
+
 static int tc_choose_splits(int M, int N, int K, int BN) {
     const int tiles = ((M + TC_BM - 1) / TC_BM) * ((N + BN - 1) / BN);
     const int nkb = (K + TC_BK - 1) / TC_BK;
     const int sms = num_sms();
-    if (tiles >= sms || nkb < 16) return 1;
-    int splits = (sms + tiles - 1) / tiles;
-    if (splits > nkb / 8) splits = nkb / 8;
-    if (splits > 32) splits = 32;
-    return splits < 1 ? 1 : splits;
+    int splits = 1;
+    if (tiles < sms && nkb >= 16) {          // fill the device
+        splits = (sms + tiles - 1) / tiles;
+        if (splits > nkb / 8) splits = nkb / 8;
+        if (splits > 32) splits = 32;
+        if (splits < 1) splits = 1;
+    }
+    const int need = (nkb + TC_CHAIN_KB - 1) / TC_CHAIN_KB;     // bound the accumulator chain
+    if (splits < need) splits = need;
+    return splits;
 }
 
 bool gemm_tc_enabled() {
