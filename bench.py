@@ -544,7 +544,15 @@ def run_ours(args, c):
     opt.run(data_dict, alis, list(warm), None)
     barrier()
     t0 = time.perf_counter()
-    opt.run(data_dict, alis, list(keys), None)
+    if os.environ.get("CTCB_BENCH_PROFILE") and rank == 0:       # where does the host spend the end-to-end run?
+        import cProfile, pstats
+        pr = cProfile.Profile()
+        pr.enable()
+        opt.run(data_dict, alis, list(keys), None)
+        pr.disable()
+        pstats.Stats(pr, stream=sys.stderr).sort_stats("cumulative").print_stats(25)
+    else:
+        opt.run(data_dict, alis, list(keys), None)
     barrier()
     e2e_t = time.perf_counter() - t0
     tt = torch.tensor([e2e_t], dtype=torch.float64, device="cuda")
