@@ -53,6 +53,9 @@ struct SweepTcArgs {
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
     int partial_own;          // 1: the partial product has its own shared-memory region (W prefetch across steps)
+    int resident;             // 1: this CTA's W slice never leaves the SM: hi half in TENSOR MEMORY (A operand of the
+                              //    .ts MMA form), lo half in shared memory; only the state is streamed (H <= 1024)
+    const float *whi[2];      // resident mode: the hi plane of the prepared (hi, lo) stack, row-major H x H
     unsigned long long *trace;   // optional (CTCB_SWEEP_TRACE): [64 steps][16] SM clock stamps of CTA (0,0,0)
 };
 constexpr int STC_TRACE_STEPS = 64;
@@ -108,6 +111,14 @@ __device__ __forceinline__ void stc_mma_tf32(uint32_t tmem_d, uint64_t adesc, ui
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// A operand from tensor memory (128 lanes = rows, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void stc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void stc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -160,12 +171,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     const int STAGES = a.stages;
     const uint32_t stage_bytes = a.stage_bytes;
     const uint32_t B_BYTES = (uint32_t)a.Npad * 128u;
+    // resident mode: [W lo: nkb x 16 KB][state ring]; streaming mode: [ring of (W hi, W lo, S hi, S lo)]
+    uint8_t *wres = base;
+    if (a.resident) base += (size_t)a.nkb * STC_A_BYTES;
+    const uint32_t s_off = a.resident ? 0u : 2 * STC_A_BYTES;         // where the state tiles sit inside a stage
     uint8_t *after_ring = base + (size_t)STAGES * stage_bytes;
     // the partial product [Npad][128] has a region of its own when it fits (then W tiles of the NEXT step may land in
     // the ring while peers still read this CTA's partial); otherwise it aliases the ring and nothing is prefetched
     float *partial = reinterpret_cast<float *>(a.partial_own ? after_ring : base);
     uint64_t *bars = reinterpret_cast<uint64_t *>(after_ring + (a.partial_own ? (size_t)a.Npad * 512 : 0));
-    uint64_t *fullW = bars, *fullS = bars + 8, *empty = bars + 16, *done = bars + 24;
+    uint64_t *fullW = bars, *fullS = bars + 8, *empty = bars + 16, *done = bars + 24, *resbar = bars + 26;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 25);
     volatile int *dead = reinterpret_cast<volatile int *>(tmem_slot + 1);
 
@@ -195,6 +210,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             stc_mbar_init(stc_smem_u32(&empty[s]), 1);
         }
         stc_mbar_init(stc_smem_u32(done), 1);
+        stc_mbar_init(stc_smem_u32(resbar), 1);
         *dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -205,7 +221,45 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     stc_fence_before();
     __syncthreads();
     stc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_a = *tmem_slot;                               // resident mode: W hi in columns [0, 32 nkb)
+    const uint32_t tmem_d = tmem_a + (a.resident ? (uint32_t)(32 * a.nkb) : 0u);
+    if (a.resident) {
+        // ---- one-time load of this CTA's 128 x (H/4) slice of W: lo half by TMA into shared memory ...
+        if (tid == 0) {
+            const uint32_t rb = stc_smem_u32(resbar);
+            stc_mbar_expect_tx(rb, (uint32_t)a.nkb * STC_A_BYTES);
+            for (int i = 0; i < a.nkb; ++i)
+                stc_tma_3d(stc_smem_u32(wres + (size_t)i * STC_A_BYTES), dir ? &tmW1 : &tmW0, rb, (blockIdx.x * a.nkb + i) * STC_BK, (blockIdx.y % a.MT) * STC_BM, 1);
+        }
+        // ---- ... hi half into tensor memory: warp w owns lanes 32 (w % 4) .. +31 (rows), warps 0-3 / 4-7 the two
+        //      halves of the columns; a thread stores 32 consecutive k of its row per tcgen05.st
+        const int row = (blockIdx.y % a.MT) * STC_BM + 32 * (warp & 3) + lane;
+        const float *wrow = a.whi[dir] + (int64_t)row * a.H + (int64_t)blockIdx.x * a.nkb * STC_BK;
+        const int ncols = 32 * a.nkb, chalf = ncols / 2;
+        for (int c0 = (warp >> 2) * chalf; c0 < (warp >> 2) * chalf + chalf; c0 += 32) {
+            uint32_t r[32];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(wrow + c0) + q);
+                r[4 * q] = __float_as_uint(v.x); r[4 * q + 1] = __float_as_uint(v.y);
+                r[4 * q + 2] = __float_as_uint(v.z); r[4 * q + 3] = __float_as_uint(v.w);
+            }
+            const uint32_t taddr = tmem_a + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)c0;
+            asm volatile(
+                "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+                "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                  "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                  "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                  "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        stc_mbar_wait(stc_smem_u32(resbar), 0, dead, a.err);
+        stc_fence_before();
+        __syncthreads();
+        stc_fence_after();
+    }
     stc_cluster_sync();
 
     // epilogue role: warp w takes columns c = w, w + 8, ... < Nc of this CTA's quarter; lane l owns units 4l..4l+3
@@ -220,7 +274,9 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         const uint32_t fb = stc_smem_u32(&fullW[st]);
         stc_mbar_expect_tx(fb, 2 * STC_A_BYTES);
         const int i = (int)(g % (uint32_t)nkb);
-        stc_tma_3d(stc_smem_u32(base + (size_t)st * stage_bytes), tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);
+        const uint32_t dst = stc_smem_u32(base + (size_t)st * stage_bytes);
+        stc_tma_3d(dst, tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);                  // hi plane
+        stc_tma_3d(dst + STC_A_BYTES, tmW, fb, (rank * nkb + i) * STC_BK, m0, 1);    // lo plane
     };
 
     for (int s = 0; s < T; ++s) {
@@ -261,14 +317,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    if (g >= gW) {            // W not prefetched: wait for the slot, then request it
+                    if (a.resident) {         // only the state travels
+                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                    } else if (g >= gW) {     // W not prefetched: wait for the slot, then request it
                         if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
                         issue_W(g);
                         gW = g + 1;
                     }
                     const uint32_t fb = stc_smem_u32(&fullS[st]);
                     stc_mbar_expect_tx(fb, 2 * B_BYTES);
-                    uint8_t *sp = base + (size_t)st * stage_bytes + 2 * STC_A_BYTES;
+                    uint8_t *sp = base + (size_t)st * stage_bytes + s_off;
                     const int k = (rank * nkb + (int)(g - g0)) * STC_BK;
                     stc_tma_3d(stc_smem_u32(sp), tmS, fb, k, b_lo, tprev);
                     stc_tma_3d(stc_smem_u32(sp + B_BYTES), tmL, fb, k, b_lo, (s - 1) & 1);
@@ -280,19 +338,32 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
+                    if (!a.resident) stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
                     stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
                     stc_fence_after();
                     if (g == g0) STC_STAMP(3);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
-                    const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
-                    const uint64_t dB = stc_smem_desc(sa + 2 * STC_A_BYTES), dBl = stc_smem_desc(sa + 2 * STC_A_BYTES + B_BYTES);
+                    const uint64_t dB = stc_smem_desc(sa + s_off), dBl = stc_smem_desc(sa + s_off + B_BYTES);
+                    if (a.resident) {
+                        const int i = (int)(g - g0);
+                        const uint64_t dAl = stc_smem_desc(stc_smem_u32(wres + (size_t)i * STC_A_BYTES));
+                        const uint32_t ta = tmem_a + (uint32_t)(32 * i);
 #pragma unroll
-                    for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
-                        const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-                        stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                        stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                               // hi . lo
-                        stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
+                        for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
+                            const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+                            stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);      // lo . hi
+                            stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dBl + adv, idesc, 1u);                         // hi . lo
+                            stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dB + adv, idesc, 1u);                          // hi . hi
+                        }
+                    } else {
+                        const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
+#pragma unroll
+                        for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
+                            const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+                            stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                            stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                               // hi . lo
+                            stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
+                        }
                     }
                     stc_commit(stc_smem_u32(&empty[st]));
                 }
@@ -305,7 +376,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
             stc_fence_after();
             if (tid == 64) STC_STAMP(5);
-            if (warp == 0 && lane == 0 && a.partial_own && s + 1 < T) {
+            if (warp == 0 && lane == 0 && a.partial_own && !a.resident && s + 1 < T) {
                 // every MMA of this step is complete, so every ring slot is free: request the first W tiles of the NEXT
                 // step now -- they travel while this CTA reduces, stores and waits at the counter barrier
                 const uint32_t gend = g1 + (uint32_t)((nkb < STAGES) ? nkb : STAGES);
@@ -389,7 +460,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     stc_cluster_sync();
     if (warp == 1) {
         stc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(a.tmem_cols) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_a), "r"(a.tmem_cols) : "memory");
     }
 }
 
@@ -437,7 +508,7 @@ static StcEncodeFn stc_encode() {
     return fn;
 }
 
-struct StcPlan { int NS, Npad, stages, tmem_cols, partial_own; uint32_t stage_bytes; size_t smem; };
+struct StcPlan { int NS, Npad, stages, tmem_cols, partial_own, resident; uint32_t stage_bytes; size_t smem; };
 
 static int stc_max_clusters(size_t smem) {
     static int cached = -1;
@@ -479,8 +550,29 @@ static bool stc_plan(int H, int B, int ndir, StcPlan *p) {
     if (Npad > 256) return false;            // would need a second utterance group per CTA and step
     NS = (B + Npad - 1) / Npad;              // drop splits that would be empty
     p->NS = NS; p->Npad = Npad;
-    p->stage_bytes = 2 * STC_A_BYTES + 2 * (uint32_t)Npad * 128u;
     const size_t partial_bytes = (size_t)Npad * 512;
+    {   // resident W: hi in tensor memory (H/4 columns beside the Npad accumulator columns), lo in shared memory
+        static int res_env = -1;   // CTCB_SWEEP_TC_RESIDENT=0 forces the streaming kernel
+        if (res_env < 0) { const char *e = getenv("CTCB_SWEEP_TC_RESIDENT"); res_env = e ? atoi(e) : 1; }
+        const int nkb = H / STC_CS / STC_BK;
+        const size_t wlo = (size_t)nkb * STC_A_BYTES;
+        const uint32_t sstage = 2 * (uint32_t)Npad * 128u;
+        if (res_env && 32 * nkb + Npad <= 512 && wlo + 2 * (size_t)sstage <= STC_SMEM_MAX && wlo + partial_bytes <= STC_SMEM_MAX) {
+            p->resident = 1;
+            p->partial_own = 0;                    // the partial aliases the state ring (nothing is prefetched into it)
+            p->stage_bytes = sstage;
+            int stages = (int)((STC_SMEM_MAX - wlo) / sstage);
+            if (stages > 6) stages = 6;
+            while ((size_t)stages * sstage < partial_bytes) ++stages;     // the ring must hold the aliased partial
+            if (wlo + (size_t)stages * sstage > STC_SMEM_MAX + 8192) return false;
+            p->stages = stages;
+            p->tmem_cols = 512;
+            p->smem = wlo + (size_t)stages * sstage + 512 + 1024;
+            return true;
+        }
+    }
+    p->resident = 0;
+    p->stage_bytes = 2 * STC_A_BYTES + 2 * (uint32_t)Npad * 128u;
     static int pf_env = -1;   // CTCB_SWEEP_TC_PREFETCH=0: never give the partial its own region (no W prefetch across steps)
     if (pf_env < 0) { const char *e = getenv("CTCB_SWEEP_TC_PREFETCH"); pf_env = e ? atoi(e) : 1; }
     // own region for the partial when at least two ring stages still fit beside it
@@ -533,7 +625,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
         {
             cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, 2};
             cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)H * H * sizeof(float)};
-            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM, 2};
+            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM, 1};      // one plane (hi or lo) per load
             cuuint32_t es[3] = {1, 1, 1};
             CUresult r = enc(&tmW[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)(stack + (size_t)dd * 2 * H * H), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -563,6 +655,8 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     a.err = counters; a.counters = counters + 16;
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
+    a.resident = p.resident;
+    a.whi[0] = stack; a.whi[1] = stack + (size_t)(ndir - 1) * 2 * H * H;
     a.trace = nullptr;
     {
         static int trace_env = -1;
