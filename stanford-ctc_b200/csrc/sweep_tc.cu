@@ -104,6 +104,13 @@ __device__ __forceinline__ void stc_tma_3d(uint32_t dst, const CUtensorMap *map,
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void stc_tma_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void stc_prefetch_map(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
 __device__ __forceinline__ void stc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -164,8 +171,7 @@ __device__ __forceinline__ uint32_t stc_idesc(int m, int n) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(STC_THREADS, 1)
 sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant__ CUtensorMap tmW1,
-                const __grid_constant__ CUtensorMap tmS0, const __grid_constant__ CUtensorMap tmS1,
-                const __grid_constant__ CUtensorMap tmL0, const __grid_constant__ CUtensorMap tmL1, SweepTcArgs a) {
+                const __grid_constant__ CUtensorMap tmR0, const __grid_constant__ CUtensorMap tmR1, SweepTcArgs a) {
     extern __shared__ __align__(1024) uint8_t stc_smem[];
     uint8_t *base = (uint8_t *)(((uintptr_t)stc_smem + 1023) & ~(uintptr_t)1023);
     const int STAGES = a.stages;
@@ -195,10 +201,13 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     const bool bptt = (a.mode == 1);
     const bool ascending = (dir == 0) != bptt;
     const CUtensorMap *tmW = dir ? &tmW1 : &tmW0;
-    const CUtensorMap *tmS = dir ? &tmS1 : &tmS0;
-    const CUtensorMap *tmL = dir ? &tmL1 : &tmL0;
+    // the state as the next step reads it: ring[parity][plane: 0 = value, 1 = low half][B][H]; ONE 4-D box fetches both
+    // planes of a k-block.  (Measured: two alternating tensor maps per k-block -- the output array for the values, a
+    // ring for the low halves -- made the TMA unit deliver one k-block per ~1250 cycles whatever its size; a single
+    // map per operand removes the descriptor switches.)
+    const CUtensorMap *tmR = dir ? &tmR1 : &tmR0;
     float *out = a.out[dir];
-    float *ring = a.ring[dir];                                        // [2][B][H]: low halves of the last two states
+    float *ring = a.ring[dir];                                        // [2 parities][2 planes][B][H]
     const float *act = a.act[dir];
     unsigned int *ctr = a.counters + (dir * a.NS + ns);
     const unsigned int domain = (unsigned int)(STC_CS * a.MT);        // CTAs that share this counter
@@ -213,6 +222,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         stc_mbar_init(stc_smem_u32(resbar), 1);
         *dead = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        stc_prefetch_map(tmW);
+        stc_prefetch_map(tmR);
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(stc_smem_u32(tmem_slot)), "r"(a.tmem_cols) : "memory");
@@ -274,9 +285,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         const uint32_t fb = stc_smem_u32(&fullW[st]);
         stc_mbar_expect_tx(fb, 2 * STC_A_BYTES);
         const int i = (int)(g % (uint32_t)nkb);
-        const uint32_t dst = stc_smem_u32(base + (size_t)st * stage_bytes);
-        stc_tma_3d(dst, tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);                  // hi plane
-        stc_tma_3d(dst + STC_A_BYTES, tmW, fb, (rank * nkb + i) * STC_BK, m0, 1);    // lo plane
+        stc_tma_3d(stc_smem_u32(base + (size_t)st * stage_bytes), tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);   // both planes
     };
 
     for (int s = 0; s < T; ++s) {
@@ -314,22 +323,26 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
                 STC_STAMP(1);
-                for (uint32_t g = g0; g < g1; ++g) {
-                    const int st = (int)(g % (uint32_t)STAGES);
-                    const uint32_t use = g / (uint32_t)STAGES;
-                    if (a.resident) {         // only the state travels
-                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                    } else if (g >= gW) {     // W not prefetched: wait for the slot, then request it
-                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                        issue_W(g);
-                        gW = g + 1;
+                // in chunks of one ring: first every W box of the chunk (one tensor map), then every state box (the other)
+                for (uint32_t c0 = g0; c0 < g1; c0 += (uint32_t)STAGES) {
+                    const uint32_t c1 = (c0 + (uint32_t)STAGES < g1) ? c0 + (uint32_t)STAGES : g1;
+                    if (!a.resident) {
+                        for (uint32_t g = (c0 > gW ? c0 : gW); g < c1; ++g) {      // not prefetched: wait for the slot, request W
+                            const uint32_t use = g / (uint32_t)STAGES;
+                            if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[g % (uint32_t)STAGES]), (use - 1) & 1, dead, a.err);
+                            issue_W(g);
+                        }
+                        if (gW < c1) gW = c1;
                     }
-                    const uint32_t fb = stc_smem_u32(&fullS[st]);
-                    stc_mbar_expect_tx(fb, 2 * B_BYTES);
-                    uint8_t *sp = base + (size_t)st * stage_bytes + s_off;
-                    const int k = (rank * nkb + (int)(g - g0)) * STC_BK;
-                    stc_tma_3d(stc_smem_u32(sp), tmS, fb, k, b_lo, tprev);
-                    stc_tma_3d(stc_smem_u32(sp + B_BYTES), tmL, fb, k, b_lo, (s - 1) & 1);
+                    for (uint32_t g = c0; g < c1; ++g) {
+                        const int st = (int)(g % (uint32_t)STAGES);
+                        const uint32_t use = g / (uint32_t)STAGES;
+                        if (a.resident && use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                        const uint32_t fb = stc_smem_u32(&fullS[st]);
+                        stc_mbar_expect_tx(fb, 2 * B_BYTES);
+                        stc_tma_4d(stc_smem_u32(base + (size_t)st * stage_bytes + s_off), tmR, fb,
+                                   (rank * nkb + (int)(g - g0)) * STC_BK, b_lo, 0, (s - 1) & 1);
+                    }
                 }
                 STC_STAMP(2);
             } else if (warp == 1 && lane == 0) {
@@ -342,6 +355,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
                     stc_fence_after();
                     if (g == g0) STC_STAMP(3);
+                    if (g == g0 + 1) STC_STAMP(14);
+                    if (g == g0 + 4) STC_STAMP(15);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dB = stc_smem_desc(sa + s_off), dBl = stc_smem_desc(sa + s_off + B_BYTES);
                     if (a.resident) {
@@ -365,6 +380,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                             stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
                         }
                     }
+                    if (g == g0) STC_STAMP(13);
                     stc_commit(stc_smem_u32(&empty[st]));
                 }
                 stc_commit(stc_smem_u32(done));
@@ -403,7 +419,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             if (tid == 64) STC_STAMP(7);
         }
         // ------------------------------------------------------------ split-K reduction over DSMEM + epilogue
-        float *ring_s = ring + (size_t)(s & 1) * B * H;
+        float *ring_s = ring + (size_t)(s & 1) * 2 * B * H;             // plane 0: the state, plane 1: its low half
 #pragma unroll
         for (int ci = 0; ci < 8; ++ci) {
             const int c = warp + 8 * ci;
@@ -432,13 +448,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
                 if (t >= Tb[ci]) v = make_float4(0.f, 0.f, 0.f, 0.f);
                 *reinterpret_cast<float4 *>(out + ((int64_t)t * B + b) * H + j4) = v;
-                if (s + 1 < T) {      // the low half the tensor cores cannot see in v: next step's second B operand
+                if (s + 1 < T) {      // the next step's B operands: v again (same tensor map as its low half) and the low half
+                    *reinterpret_cast<float4 *>(ring_s + (int64_t)b * H + j4) = v;
                     float4 lo;
                     lo.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
                     lo.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
                     lo.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
                     lo.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-                    *reinterpret_cast<float4 *>(ring_s + (int64_t)b * H + j4) = lo;
+                    *reinterpret_cast<float4 *>(ring_s + (int64_t)(B + b) * H + j4) = lo;
                 }
             }
         }
@@ -597,7 +614,7 @@ static bool stc_enabled(int H) {
 
 // scratch: (hi, lo) stacks of both recurrent matrices, the rings of state low halves, the optional trace
 static size_t stc_ws_stack_bytes(int H) { return align_up((size_t)4 * H * H * sizeof(float), 1024); }
-static size_t stc_ws_ring_bytes(int H, int B) { return align_up((size_t)4 * B * H * sizeof(float), 1024); }
+static size_t stc_ws_ring_bytes(int H, int B) { return align_up((size_t)8 * B * H * sizeof(float), 1024); }
 size_t sweep_tc_workspace_bytes(int H, int B) {
     return stc_ws_stack_bytes(H) + stc_ws_ring_bytes(H, B) + STC_TRACE_STEPS * 16 * 8 + 1024;
 }
@@ -619,13 +636,13 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
         CTCB_LAUNCH_CHECK();
     }
     float *outs[2] = {outF, Wb ? outB : outF};
-    CUtensorMap tmW[2], tmS[2], tmL[2];
+    CUtensorMap tmW[2], tmR[2];
     for (int d = 0; d < 2; ++d) {
         const int dd = (d < ndir) ? d : 0;
         {
             cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)H, 2};
             cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)H * H * sizeof(float)};
-            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM, 1};      // one plane (hi or lo) per load
+            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)STC_BM, (cuuint32_t)(p.resident ? 1 : 2)};   // resident: lo plane only
             cuuint32_t es[3] = {1, 1, 1};
             CUresult r = enc(&tmW[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)(stack + (size_t)dd * 2 * H * H), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -633,25 +650,20 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
             if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(W) failed (%d)", (int)r);
         }
         {
-            cuuint64_t dims[3] = {(cuuint64_t)H, (cuuint64_t)B, (cuuint64_t)T};
-            cuuint64_t strides[2] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)B * H * sizeof(float)};
-            cuuint32_t box[3] = {(cuuint32_t)STC_BK, (cuuint32_t)p.Npad, 1};
-            cuuint32_t es[3] = {1, 1, 1};
-            CUresult r = enc(&tmS[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)outs[dd], dims, strides, box, es,
+            cuuint64_t dims[4] = {(cuuint64_t)H, (cuuint64_t)B, 2, 2};
+            cuuint64_t strides[3] = {(cuuint64_t)H * sizeof(float), (cuuint64_t)B * H * sizeof(float), (cuuint64_t)2 * B * H * sizeof(float)};
+            cuuint32_t box[4] = {(cuuint32_t)STC_BK, (cuuint32_t)p.Npad, 2, 1};
+            cuuint32_t es[4] = {1, 1, 1, 1};
+            CUresult r = enc(&tmR[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)(ring + (size_t)dd * 4 * B * H), dims, strides, box, es,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state) failed (%d)", (int)r);
-            dims[2] = 2;
-            r = enc(&tmL[d], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void *)(ring + (size_t)dd * 2 * B * H), dims, strides, box, es,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state lo) failed (%d)", (int)r);
+            if (r != CUDA_SUCCESS) return set_error(CTCB_ECUDA, "sweep_tc: cuTensorMapEncodeTiled(state ring) failed (%d)", (int)r);
         }
     }
     SweepTcArgs a;
     a.mode = mode; a.T = T; a.B = B; a.H = H; a.Tlen = Tlen; a.pre = pre;
     a.out[0] = outs[0]; a.out[1] = outs[1]; a.act[0] = actF; a.act[1] = Wb ? actB : actF; a.maxAct = maxAct;
-    a.ring[0] = ring; a.ring[1] = ring + (size_t)(ndir - 1) * 2 * B * H;
+    a.ring[0] = ring; a.ring[1] = ring + (size_t)(ndir - 1) * 4 * B * H;
     a.err = counters; a.counters = counters + 16;
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
@@ -679,7 +691,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     static int coop = -1;     // does this driver accept cluster + cooperative together?
     if (coop != 0) {
         cfg.numAttrs = 2;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], tmL[0], tmL[1], a);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmR[0], tmR[1], a);
         if (e == cudaSuccess) { coop = 1; count_launch(); *handled = true; return CTCB_OK; }
         cudaGetLastError();
         if (coop == 1) return set_error(CTCB_ECUDA, "sweep_tc: launch failed: %s", cudaGetErrorString(e));
@@ -687,7 +699,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
         if (getenv("CTCB_DEBUG")) fprintf(stderr, "[ctcb] tensor-core sweep: cooperative+cluster launch refused (%s), plain cluster launch\n", cudaGetErrorString(e));
     }
     cfg.numAttrs = 1;         // grid <= one wave of clusters by construction (stc_plan)
-    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmS[0], tmS[1], tmL[0], tmL[1], a));
+    CTCB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmR[0], tmR[1], a));
     count_launch();
     *handled = true;
     return CTCB_OK;

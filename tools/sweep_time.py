@@ -31,17 +31,19 @@ for name, fn in (("fwd", fwd), ("bptt", bwd)):
 
 if os.environ.get("CTCB_SWEEP_TRACE"):
     al = lambda x: (x + 1023) // 1024 * 1024
-    off = (4096 + al(4 * H * H * 4) + al(4 * B * H * 4)) // 8
+    off = (4096 + al(4 * H * H * 4) + al(8 * B * H * 4)) // 8
     tr = scr.view(torch.int64)[off:off + 64 * 16].cpu().numpy().reshape(64, 16)
     names = ["step top", "counter seen", "TMA issued", "first ready (MMA)", "done commit issued", "done seen (epi)",
              "partial in smem", "after cluster sync", "after finalize stores", "after syncthreads", "after arrive",
-             "first full (splitter)", "last full (splitter)"]
+             "-", "-", "k-block 0 MMAs issued", "k-block 1 data seen", "k-block 4 data seen"]
     import numpy as np
     rows = tr[8:56]
     base = rows[:, 0:1]
-    rel = (rows[:, :13] - base).astype(np.float64)
+    rel = (rows[:, :16] - base).astype(np.float64)
     med = np.median(rel, axis=0)
     period = np.median(np.diff(tr[8:56, 0]))
     print("trace of CTA (0,0,0), last launch (BPTT), SM cycles relative to the step top, median over steps 8..55; step period %.0f cycles" % period)
     for i in np.argsort(med):
+        if names[i] == "-":
+            continue
         print("  %-24s %8.0f" % (names[i], med[i]))
