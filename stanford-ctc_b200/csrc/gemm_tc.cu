@@ -203,7 +203,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&ready[s]), (uint32_t)(use & 1));      // hi landed and lo written
-                tc_fence_after();
+                if (i == 0) tc_fence_after();   // once: a fence per k-block drains the MMAs already issued (sweep_tc.cu)
                 const uint32_t a = tc_smem_u32(base + s * STAGE_BYTES);
                 const uint64_t dA = g.a_mn ? tc_smem_desc_mn(a) : tc_smem_desc(a);
                 const uint64_t dAl = g.a_mn ? tc_smem_desc_mn(a + A_BYTES) : tc_smem_desc(a + A_BYTES);

@@ -323,26 +323,20 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 } while (true);
                 asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
                 STC_STAMP(1);
-                // in chunks of one ring: first every W box of the chunk (one tensor map), then every state box (the other)
-                for (uint32_t c0 = g0; c0 < g1; c0 += (uint32_t)STAGES) {
-                    const uint32_t c1 = (c0 + (uint32_t)STAGES < g1) ? c0 + (uint32_t)STAGES : g1;
-                    if (!a.resident) {
-                        for (uint32_t g = (c0 > gW ? c0 : gW); g < c1; ++g) {      // not prefetched: wait for the slot, request W
-                            const uint32_t use = g / (uint32_t)STAGES;
-                            if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[g % (uint32_t)STAGES]), (use - 1) & 1, dead, a.err);
-                            issue_W(g);
-                        }
-                        if (gW < c1) gW = c1;
+                for (uint32_t g = g0; g < g1; ++g) {
+                    const int st = (int)(g % (uint32_t)STAGES);
+                    const uint32_t use = g / (uint32_t)STAGES;
+                    if (a.resident) {         // only the state travels
+                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                    } else if (g >= gW) {     // W not prefetched: wait for the slot, then request it
+                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                        issue_W(g);
+                        gW = g + 1;
                     }
-                    for (uint32_t g = c0; g < c1; ++g) {
-                        const int st = (int)(g % (uint32_t)STAGES);
-                        const uint32_t use = g / (uint32_t)STAGES;
-                        if (a.resident && use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                        const uint32_t fb = stc_smem_u32(&fullS[st]);
-                        stc_mbar_expect_tx(fb, 2 * B_BYTES);
-                        stc_tma_4d(stc_smem_u32(base + (size_t)st * stage_bytes + s_off), tmR, fb,
-                                   (rank * nkb + (int)(g - g0)) * STC_BK, b_lo, 0, (s - 1) & 1);
-                    }
+                    const uint32_t fb = stc_smem_u32(&fullS[st]);
+                    stc_mbar_expect_tx(fb, 2 * B_BYTES);
+                    stc_tma_4d(stc_smem_u32(base + (size_t)st * stage_bytes + s_off), tmR, fb,
+                               (rank * nkb + (int)(g - g0)) * STC_BK, b_lo, 0, (s - 1) & 1);
                 }
                 STC_STAMP(2);
             } else if (warp == 1 && lane == 0) {
@@ -353,7 +347,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     const uint32_t use = g / (uint32_t)STAGES;
                     if (!a.resident) stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
                     stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
-                    stc_fence_after();
+                    // ONE tcgen05 fence per step (it orders this step's MMAs behind the epilogue's tensor-memory reads of
+                    // the previous one).  A fence after every ring wait made the issuing thread drain the 12 MMAs of the
+                    // previous k-block first: issue (~800 cycles) and execution (~500) ran back to back, 1250-1300 cycles
+                    // per k-block in every configuration (profiles/sweep_tc_trace_r2.txt).
+                    if (g == g0) stc_fence_after();
                     if (g == g0) STC_STAMP(3);
                     if (g == g0 + 1) STC_STAMP(14);
                     if (g == g0 + 4) STC_STAMP(15);
