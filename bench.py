@@ -540,7 +540,7 @@ def run_ours(args, c):
     pool_d, pool_l = make_batch(c, min(len(keys), 4 * Bg), seed=77)
     data_dict = {k: pool_d[i % len(pool_d)] for i, k in enumerate(keys)}
     alis = {k: pool_l[i % len(pool_l)] for i, k in enumerate(keys)}
-    warm = keys[:Bg * 2]
+    warm = keys[:Bg * min(8, e2e_steps)]       # long enough for both staging buffers' step graphs to be captured
     opt.run(data_dict, alis, list(warm), None)
     barrier()
     t0 = time.perf_counter()
@@ -628,6 +628,37 @@ def run_ours(args, c):
     sweep_tab = None
     if rank == 0 and world == 1 and not args.headline_only:
         sweep_tab = ctc_sweep_table(torch, pk)
+    # ---------------------------------------------------------------- ragged-T variant (+-20 % uniform T)
+    ragged = None
+    if world == 1 and not args.headline_only:
+        ragged = {}
+        rng = np.random.RandomState(5)
+        nutt = Bg * 40
+        Ts = rng.randint(int(0.8 * c["T"]), int(1.2 * c["T"]) + 1, size=nutt)
+        rkeys = ["r%05d" % i for i in range(nutt)]
+        rdata = {k: np.asfortranarray(rng.randn(c["D"], int(t)).astype(np.float32)) for k, t in zip(rkeys, Ts)}
+        ralis = {k: (1 + np.floor(rng.rand(c["L"]) * (c["K"] - 1))).astype(np.int32) for k in rkeys}
+        cr = dict(c, Tmax=int(1.2 * c["T"]) + 1)
+        for tag, pool in (("bucketed", 16), ("plain_chunks", 0)):
+            nn_r, opt_r = _mk_net(cr, Bg, Bg, world)
+            opt_r.bucketPool = pool
+            opt_r.it = 11
+            import random as _random
+            _random.seed(33)
+            opt_r.run(rdata, ralis, list(rkeys[:Bg * 8]), None)
+            torch.cuda.synchronize()
+            opt_r.padded_frames = opt_r.real_frames = 0
+            t0 = time.perf_counter()
+            opt_r.run(rdata, ralis, list(rkeys), None)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ragged[tag] = {"utterances_per_s": nutt / dt, "real_frames_per_s": opt_r.real_frames / dt,
+                           "padded_over_real_frames": opt_r.padded_frames / float(opt_r.real_frames)}
+            del nn_r, opt_r
+            torch.cuda.empty_cache()
+        ragged["note"] = ("end to end through SGD.run on %d utterances with T ~ U[0.8, 1.2] x %d; 'bucketed' = pools of 16 "
+                          "minibatches sorted by length (sgd.SGD.bucketPool), 'plain_chunks' = consecutive chunks of the shuffled list"
+                          % (nutt, c["T"]))
 
     # ---------------------------------------------------------------- CPU baseline (rank 0, N=1 only)
     cpu = None
@@ -662,7 +693,7 @@ def run_ours(args, c):
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall,
             "model_tflops": value * flops_per_utt(c) / 1e12,
             "phases_ms": phases, "roofline": roof, "roofline_ctc": roof_ctc, "cpu_baseline": cpu,
-            "configs": extra, "ctc_sweep": sweep_tab,
+            "configs": extra, "ctc_sweep": sweep_tab, "ragged_T": ragged,
             "strong_scaling_note": "configs.*_strong_b256 hold a FIXED global batch of 256 utterances split over n_gpus: "
                                    "speed-up at N = value(N) / value(1) of the same key; north_star's target is >= 6x at 8",
         }

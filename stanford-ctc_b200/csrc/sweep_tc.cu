@@ -53,6 +53,7 @@ struct SweepTcArgs {
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
     int partial_own;          // 1: the partial product has its own shared-memory region (W prefetch across steps)
+    int nomma;                // experiment (CTCB_SWEEP_TC_NOMMA=1): issue no MMA -- how fast does the operand stream alone run?
     int resident;             // 1: this CTA's W slice never leaves the SM: hi half in TENSOR MEMORY (A operand of the
                               //    .ts MMA form), lo half in shared memory; only the state is streamed (H <= 1024)
     const float *whi[2];      // resident mode: the hi plane of the prepared (hi, lo) stack, row-major H x H
@@ -357,7 +358,8 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     if (g == g0 + 4) STC_STAMP(15);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dB = stc_smem_desc(sa + s_off), dBl = stc_smem_desc(sa + s_off + B_BYTES);
-                    if (a.resident) {
+                    if (a.nomma) {
+                    } else if (a.resident) {
                         const int i = (int)(g - g0);
                         const uint64_t dAl = stc_smem_desc(stc_smem_u32(wres + (size_t)i * STC_A_BYTES));
                         const uint32_t ta = tmem_a + (uint32_t)(32 * i);
@@ -666,6 +668,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
     a.resident = p.resident;
+    { static int nm = -1; if (nm < 0) { const char *e = getenv("CTCB_SWEEP_TC_NOMMA"); nm = e ? atoi(e) : 0; } a.nomma = nm; }
     a.whi[0] = stack; a.whi[1] = stack + (size_t)(ndir - 1) * 2 * H * H;
     a.trace = nullptr;
     {
