@@ -43,7 +43,8 @@ class SGD:
         # chunks of the shuffled list); padded_frames / real_frames accumulate what the padding costs
         self.bucketPool = bucketPool
         # CUDA graphs: one launch per step instead of ~40 (see step_device)
-        self.useGraphs = True
+        import os as _os
+        self.useGraphs = not _os.environ.get("CTCB_NO_GRAPH")      # e.g. under a profiler that wants plain launches
         self._graphs = {}
         self._graph_seen = {}
         self._stream = None
