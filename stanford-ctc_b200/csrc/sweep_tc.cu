@@ -415,6 +415,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             }
             stc_fence_before();
             if (tid == 64) STC_STAMP(6);
+            __syncthreads();         // implied by the cluster barrier below; stated for tools that only model CTA barriers
             stc_cluster_sync();      // all four partials of this (M tile, split) are in shared memory
             if (tid == 64) STC_STAMP(7);
         }
@@ -689,7 +690,8 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     attr[1].id = cudaLaunchAttributeCooperative;       // co-residency of all CTAs (they meet at the counter barrier)
     attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    static int coop = -1;     // does this driver accept cluster + cooperative together?
+    static int coop = -1;     // does this driver accept cluster + cooperative together?  (CTCB_SWEEP_TC_COOP=0: plain cluster launch)
+    if (coop < 0) { const char *e = getenv("CTCB_SWEEP_TC_COOP"); if (e && atoi(e) == 0) coop = 0; }
     if (coop != 0) {
         cfg.numAttrs = 2;
         cudaError_t e = cudaLaunchKernelEx(&cfg, sweep_tc_kernel, tmW[0], tmW[1], tmR[0], tmR[1], a);
