@@ -97,6 +97,16 @@ __device__ __forceinline__ void stc_mbar_wait(uint32_t bar, uint32_t parity, vol
         }
     }
 }
+// One lane of a CONVERGED warp.  The producer and MMA roles run their loops with the whole warp (warp-uniform control
+// flow and operands) and only ISSUE from the elected lane: inside a `lane == 0` branch the compiler must assume
+// divergent descriptors and wraps every UTCHMMA / UTMALDG / UTCBAR in an ELECT + R2UR.BROADCAST waterfall loop --
+// measured 69 cycles per MMA issue and ~400 per commit instead of the tensor core's 48 per MMA
+// (profiles/sweep_tc_trace_r2.txt, ncu source page).
+__device__ __forceinline__ bool stc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void stc_tma_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
@@ -311,80 +321,91 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
         }
         if (s > 0) {
             const uint32_t g0 = (uint32_t)(s - 1) * (uint32_t)nkb, g1 = g0 + (uint32_t)nkb;
-            if (warp == 0 && lane == 0) {
-                // ---------------------------------------------------- TMA producer
-                STC_STAMP(0);
+            if (warp == 0) {
+                // ---------------------------------------------------- TMA producer (whole warp, elected issue)
+                const bool leader = stc_elect_one();
+                if (leader) STC_STAMP(0);
                 const unsigned int target = domain * (unsigned int)s;
-                unsigned int v;
-                const long long t0 = clock64();
-                do {
-                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
-                    if (v >= target || *dead) break;
-                    if (clock64() - t0 > 2000000000LL) { *dead = 1; atomicExch(a.err, 3u); break; }
-                } while (true);
-                asm volatile("fence.proxy.async;" ::: "memory");      // peers' generic-proxy stores -> this CTA's TMA reads
-                STC_STAMP(1);
+                if (leader) {
+                    unsigned int v;
+                    const long long t0 = clock64();
+                    do {
+                        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+                        if (v >= target || *dead) break;
+                        if (clock64() - t0 > 2000000000LL) { *dead = 1; atomicExch(a.err, 3u); break; }
+                    } while (true);
+                    asm volatile("fence.proxy.async;" ::: "memory");  // peers' generic-proxy stores -> this CTA's TMA reads
+                    STC_STAMP(1);
+                }
+                __syncwarp();
                 for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    if (a.resident) {         // only the state travels
-                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                    } else if (g >= gW) {     // W not prefetched: wait for the slot, then request it
-                        if (use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
-                        issue_W(g);
-                        gW = g + 1;
-                    }
+                    const bool need_w = !a.resident && g >= gW;
+                    if ((a.resident || need_w) && use > 0) stc_mbar_wait(stc_smem_u32(&empty[st]), (use - 1) & 1, dead, a.err);
+                    if (need_w) gW = g + 1;
                     const uint32_t fb = stc_smem_u32(&fullS[st]);
-                    stc_mbar_expect_tx(fb, 2 * B_BYTES);
-                    stc_tma_4d(stc_smem_u32(base + (size_t)st * stage_bytes + s_off), tmR, fb,
-                               (rank * nkb + (int)(g - g0)) * STC_BK, b_lo, 0, (s - 1) & 1);
+                    const uint32_t sdst = stc_smem_u32(base + (size_t)st * stage_bytes + s_off);
+                    const int kc = (rank * nkb + (int)(g - g0)) * STC_BK;
+                    if (leader && a.nomma != 2) {
+                        if (need_w) issue_W(g);
+                        stc_mbar_expect_tx(fb, 2 * B_BYTES);
+                        stc_tma_4d(sdst, tmR, fb, kc, b_lo, 0, (s - 1) & 1);
+                    }
                 }
-                STC_STAMP(2);
-            } else if (warp == 1 && lane == 0) {
-                // ---------------------------------------------------- MMA issuer
+                if (leader) STC_STAMP(2);
+                __syncwarp();
+            } else if (warp == 1) {
+                // ---------------------------------------------------- MMA issuer (whole warp, elected issue)
+                const bool leader = stc_elect_one();
                 const uint32_t idesc = stc_idesc(STC_BM, Npad);
                 for (uint32_t g = g0; g < g1; ++g) {
                     const int st = (int)(g % (uint32_t)STAGES);
                     const uint32_t use = g / (uint32_t)STAGES;
-                    if (!a.resident) stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
-                    stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
+                    if (!a.resident && a.nomma != 2) stc_mbar_wait(stc_smem_u32(&fullW[st]), use & 1, dead, a.err);
+                    if (a.nomma != 2) stc_mbar_wait(stc_smem_u32(&fullS[st]), use & 1, dead, a.err);
                     // ONE tcgen05 fence per step (it orders this step's MMAs behind the epilogue's tensor-memory reads of
-                    // the previous one).  A fence after every ring wait made the issuing thread drain the 12 MMAs of the
-                    // previous k-block first: issue (~800 cycles) and execution (~500) ran back to back, 1250-1300 cycles
-                    // per k-block in every configuration (profiles/sweep_tc_trace_r2.txt).
+                    // the previous one)
                     if (g == g0) stc_fence_after();
-                    if (g == g0) STC_STAMP(3);
-                    if (g == g0 + 1) STC_STAMP(14);
-                    if (g == g0 + 4) STC_STAMP(15);
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dB = stc_smem_desc(sa + s_off), dBl = stc_smem_desc(sa + s_off + B_BYTES);
-                    if (a.nomma) {
-                    } else if (a.resident) {
-                        const int i = (int)(g - g0);
-                        const uint64_t dAl = stc_smem_desc(stc_smem_u32(wres + (size_t)i * STC_A_BYTES));
-                        const uint32_t ta = tmem_a + (uint32_t)(32 * i);
+                    const int i = (int)(g - g0);
+                    const uint64_t dAlr = stc_smem_desc(stc_smem_u32(wres + (size_t)i * STC_A_BYTES));
+                    const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
+                    const uint32_t ta = tmem_a + (uint32_t)(32 * i);
+                    const uint32_t eb = stc_smem_u32(&empty[st]);
+                    if (leader) {
+                        if (g == g0) STC_STAMP(3);
+                        if (g == g0 + 1) STC_STAMP(14);
+                        if (g == g0 + 4) STC_STAMP(15);
+                        if (a.nomma == 1) {
+                        } else if (a.resident) {
 #pragma unroll
-                        for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
-                            const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-                            stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);      // lo . hi
-                            stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dBl + adv, idesc, 1u);                         // hi . lo
-                            stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dB + adv, idesc, 1u);                          // hi . hi
-                        }
-                    } else {
-                        const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
+                            for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
+                                const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+                                stc_mma_tf32(tmem_d, dAlr + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);     // lo . hi
+                                stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dBl + adv, idesc, 1u);                         // hi . lo
+                                stc_mma_tf32_ts(tmem_d, ta + 8 * k8, dB + adv, idesc, 1u);                          // hi . hi
+                            }
+                        } else {
 #pragma unroll
-                        for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
-                            const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
-                            stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                            stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                               // hi . lo
-                            stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
+                            for (int k8 = 0; k8 < STC_BK / 8; ++k8) {
+                                const uint64_t adv = (uint64_t)((k8 * 32) >> 4);
+                                stc_mma_tf32(tmem_d, dAl + adv, dB + adv, idesc, (g > g0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                                stc_mma_tf32(tmem_d, dA + adv, dBl + adv, idesc, 1u);                               // hi . lo
+                                stc_mma_tf32(tmem_d, dA + adv, dB + adv, idesc, 1u);                                // hi . hi
+                            }
                         }
+                        if (g == g0) STC_STAMP(13);
+                        stc_commit(eb);
                     }
-                    if (g == g0) STC_STAMP(13);
-                    stc_commit(stc_smem_u32(&empty[st]));
+                    __syncwarp();
                 }
-                stc_commit(stc_smem_u32(done));
-                STC_STAMP(4);
+                if (leader) {
+                    stc_commit(stc_smem_u32(done));
+                    STC_STAMP(4);
+                }
+                __syncwarp();
             }
             gM = g1;
             __syncwarp();
@@ -392,12 +413,14 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
             stc_fence_after();
             if (tid == 64) STC_STAMP(5);
-            if (warp == 0 && lane == 0 && a.partial_own && !a.resident && s + 1 < T) {
+            if (warp == 0 && a.partial_own && !a.resident && s + 1 < T) {
                 // every MMA of this step is complete, so every ring slot is free: request the first W tiles of the NEXT
                 // step now -- they travel while this CTA reduces, stores and waits at the counter barrier
                 const uint32_t gend = g1 + (uint32_t)((nkb < STAGES) ? nkb : STAGES);
-                for (uint32_t g = g1; g < gend; ++g) issue_W(g);
+                if (stc_elect_one() && a.nomma != 2)
+                    for (uint32_t g = g1; g < gend; ++g) issue_W(g);
                 gW = gend;
+                __syncwarp();
             }
             {
                 const int q = warp & 3, half = warp >> 2;
