@@ -87,6 +87,14 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
+// One lane of a converged warp: the producer and MMA loops run warp-uniform and only ISSUE from the elected lane.  Inside a
+// `lane == 0` branch the compiler wraps every UTCHMMA / UTMALDG / UTCBAR in an ELECT + R2UR.BROADCAST loop (69 cycles per
+// MMA issue, measured in sweep_tc.cu) -- slower than the 48-64 cycles an MMA of a 64- or 128-wide tile takes to execute.
+__device__ __forceinline__ bool tc_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.b32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -173,30 +181,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_d = *tmem_slot;
 
     if (nkb > 0) {
-        if (warp == 0 && lane == 0) {
-            // ------------------------------------------------------------ TMA producer
+        if (warp == 0) {
+            // ------------------------------------------------------------ TMA producer (whole warp, elected issue)
+            const bool leader = tc_elect_one();
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 if (use > 0) tc_mbar_wait(tc_smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
                 const uint32_t full = tc_smem_u32(&bars[s]);
-                tc_mbar_expect_tx(full, A_BYTES + B_BYTES);
-                uint8_t *st = base + s * STAGE_BYTES;
+                const uint32_t sa = tc_smem_u32(base + s * STAGE_BYTES), sb = sa + 2 * A_BYTES;
                 const int k = (kb0 + i) * TC_BK;
-                if (g.a_mn) {      // four boxes of {32 m, 32 k}
+                if (leader) {
+                    tc_mbar_expect_tx(full, A_BYTES + B_BYTES);
+                    if (g.a_mn) {      // four boxes of {32 m, 32 k}
 #pragma unroll
-                    for (int j = 0; j < TC_BM / 32; ++j) tc_tma_load_2d(tc_smem_u32(st + j * 4096), &tmA, full, m0 + 32 * j, k);
-                } else {
-                    tc_tma_load_2d(tc_smem_u32(st), &tmA, full, k, m0);
-                }
-                if (g.b_mn) {
+                        for (int j = 0; j < TC_BM / 32; ++j) tc_tma_load_2d(sa + j * 4096, &tmA, full, m0 + 32 * j, k);
+                    } else {
+                        tc_tma_load_2d(sa, &tmA, full, k, m0);
+                    }
+                    if (g.b_mn) {
 #pragma unroll
-                    for (int j = 0; j < BN / 32; ++j) tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES + j * 4096), &tmB, full, n0 + 32 * j, k);
-                } else {
-                    tc_tma_load_2d(tc_smem_u32(st + 2 * A_BYTES), &tmB, full, k, n0);
+                        for (int j = 0; j < BN / 32; ++j) tc_tma_load_2d(sb + j * 4096, &tmB, full, n0 + 32 * j, k);
+                    } else {
+                        tc_tma_load_2d(sb, &tmB, full, k, n0);
+                    }
                 }
+                __syncwarp();
             }
-        } else if (warp == 1 && lane == 0) {
-            // ------------------------------------------------------------ MMA issuer
+        } else if (warp == 1) {
+            // ------------------------------------------------------------ MMA issuer (whole warp, elected issue)
+            const bool leader = tc_elect_one();
             const uint32_t idesc = tc_idesc(TC_BM, BN, g.a_mn, g.b_mn);
             // per k-step (8 floats of K): 32 bytes along the swizzled row (K-major) or one whole 1 KB atom (MN-major)
             const uint64_t stepA = (uint64_t)((g.a_mn ? 1024 : 32) >> 4), stepB = (uint64_t)((g.b_mn ? 1024 : 32) >> 4);
@@ -209,20 +222,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t dAl = g.a_mn ? tc_smem_desc_mn(a + A_BYTES) : tc_smem_desc(a + A_BYTES);
                 const uint64_t dB = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES) : tc_smem_desc(a + 2 * A_BYTES);
                 const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES + B_BYTES) : tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
+                const uint32_t eb = tc_smem_u32(&bars[STAGES + s]);
+                if (leader) {
 #pragma unroll
-                for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
-                    const uint64_t aa = (uint64_t)k8 * stepA, ab = (uint64_t)k8 * stepB;
-                    if (g.nmma >= 3) {
-                        tc_mma_tf32(tmem_d, dAl + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
-                        tc_mma_tf32(tmem_d, dA + aa, dBl + ab, idesc, 1u);                              // hi . lo
-                        tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, 1u);                               // hi . hi
-                    } else {
-                        tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
+                    for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                        const uint64_t aa = (uint64_t)k8 * stepA, ab = (uint64_t)k8 * stepB;
+                        if (g.nmma >= 3) {
+                            tc_mma_tf32(tmem_d, dAl + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                            tc_mma_tf32(tmem_d, dA + aa, dBl + ab, idesc, 1u);                              // hi . lo
+                            tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, 1u);                               // hi . hi
+                        } else {
+                            tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
+                        }
                     }
+                    tc_commit(eb);                                 // slot free once these MMAs have read it
                 }
-                tc_commit(tc_smem_u32(&bars[STAGES + s]));         // slot free once these MMAs have read it
+                __syncwarp();
             }
-            tc_commit(tc_smem_u32(&bars[2 * STAGES]));             // accumulator complete
+            if (leader) tc_commit(tc_smem_u32(&bars[2 * STAGES])); // accumulator complete
+            __syncwarp();
         } else if (warp >= 4) {
             // ------------------------------------------------------------ splitters (TC_SPLIT_WARPS warps)
             constexpr int NSPLIT = 32 * TC_SPLIT_WARPS;
