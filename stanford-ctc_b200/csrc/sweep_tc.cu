@@ -53,6 +53,7 @@ struct SweepTcArgs {
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
     int partial_own;          // 1: the partial product has its own shared-memory region (W prefetch across steps)
+    int rotate;               // experiment (CTCB_SWEEP_TC_ROTATE=1): M-tile CTAs walk the k-blocks in rotated orders; measured: no effect
     int nomma;                // experiment (CTCB_SWEEP_TC_NOMMA=1): issue no MMA -- how fast does the operand stream alone run?
     int resident;             // 1: this CTA's W slice never leaves the SM: hi half in TENSOR MEMORY (A operand of the
                               //    .ts MMA form), lo half in shared memory; only the state is streamed (H <= 1024)
@@ -290,12 +291,16 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     uint32_t gW = 0;              // producer: next job whose W tiles have not been requested yet
     uint32_t gM = 0;              // MMA issuer: next job to multiply
 
+    // The 8 (16) M-tile CTAs of a (direction, split, K-slice) all need the SAME state tiles: each starts its walk over the
+    // k-blocks at a different one, so that they do not ask L2 for the same lines at the same moment.
+    const int kb_rot = a.rotate ? mt : 0;
+    auto kb_of = [&](uint32_t g) { return (int)((g % (uint32_t)nkb + (uint32_t)kb_rot) % (uint32_t)nkb); };
     // issue the W tiles (hi + lo in one 3-D box) of job g; the caller guarantees the slot is free
     auto issue_W = [&](uint32_t g) {
         const int st = (int)(g % (uint32_t)STAGES);
         const uint32_t fb = stc_smem_u32(&fullW[st]);
         stc_mbar_expect_tx(fb, 2 * STC_A_BYTES);
-        const int i = (int)(g % (uint32_t)nkb);
+        const int i = kb_of(g);
         stc_tma_3d(stc_smem_u32(base + (size_t)st * stage_bytes), tmW, fb, (rank * nkb + i) * STC_BK, m0, 0);   // both planes
     };
 
@@ -346,7 +351,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     if (need_w) gW = g + 1;
                     const uint32_t fb = stc_smem_u32(&fullS[st]);
                     const uint32_t sdst = stc_smem_u32(base + (size_t)st * stage_bytes + s_off);
-                    const int kc = (rank * nkb + (int)(g - g0)) * STC_BK;
+                    const int kc = (rank * nkb + kb_of(g)) * STC_BK;
                     if (leader && a.nomma != 2) {
                         if (need_w) issue_W(g);
                         stc_mbar_expect_tx(fb, 2 * B_BYTES);
@@ -369,7 +374,7 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                     if (g == g0) stc_fence_after();
                     const uint32_t sa = stc_smem_u32(base + (size_t)st * stage_bytes);
                     const uint64_t dB = stc_smem_desc(sa + s_off), dBl = stc_smem_desc(sa + s_off + B_BYTES);
-                    const int i = (int)(g - g0);
+                    const int i = kb_of(g);
                     const uint64_t dAlr = stc_smem_desc(stc_smem_u32(wres + (size_t)i * STC_A_BYTES));
                     const uint64_t dA = stc_smem_desc(sa), dAl = stc_smem_desc(sa + STC_A_BYTES);
                     const uint32_t ta = tmem_a + (uint32_t)(32 * i);
@@ -692,6 +697,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
     a.resident = p.resident;
+    { static int ro = -1; if (ro < 0) { const char *e = getenv("CTCB_SWEEP_TC_ROTATE"); ro = e ? atoi(e) : 0; } a.rotate = ro; }
     { static int nm = -1; if (nm < 0) { const char *e = getenv("CTCB_SWEEP_TC_NOMMA"); nm = e ? atoi(e) : 0; } a.nomma = nm; }
     a.whi[0] = stack; a.whi[1] = stack + (size_t)(ndir - 1) * 2 * H * H;
     a.trace = nullptr;
