@@ -622,6 +622,9 @@ def run_ours(args, c):
         # BASELINE.json configs[3]: 5-layer BRNN hidden=2048, global batch 256, T=1500 (on 8 GPUs: 32 per GPU)
         c4 = CONFIGS["c4"]
         extra["c4_strong_b256"] = _run_config(torch, dist, world, rank, c4, c4["B"], 3, 3, flush, profile=2)
+        # the reference's real TIMIT input width: 41 features x 23 context frames (timit-utils/runTimit.sh:21)
+        c2w = dict(CONFIGS["c2"], D=943, name="C2 with the reference's real TIMIT input width D = 41 x 23 = 943, B=32/GPU")
+        extra["c2_input_d943_weak"] = _run_config(torch, dist, world, rank, c2w, c2w["B"] * world, 20, 3, flush)
         for k_, v_ in extra.items():
             v_["scaling"] = "weak" if k_.endswith("weak") else "strong"
             v_["n_gpus"] = world

@@ -56,10 +56,35 @@ def ctc_loss_batch(acts, T_per_utt, labels, label_off, max_labels, blank=0, is_p
     return nll, grad, skip
 
 
+_scratch = {}
+
+
+def _single_utterance_buffers(torch, dev, T, K, L):
+    """Device and pinned-host buffers of the reference-signature call, kept per (T, K, |l|): a reference user who steps
+    one utterance at a time (sgd.py:70-161) re-uses them instead of allocating seven tensors per call."""
+    key = (dev.index, T, K, L)
+    b = _scratch.get(key)
+    if b is None:
+        if len(_scratch) > 64:
+            _scratch.clear()
+        n_int = 3 + max(L, 1)                               # label_off[2], T, labels
+        b = dict(h_acts=torch.empty(T * K, dtype=torch.float32).pin_memory(),
+                 h_int=torch.empty(n_int, dtype=torch.int32).pin_memory(),
+                 h_grad=torch.empty(T * K, dtype=torch.float32).pin_memory(),
+                 h_out=torch.empty(2, dtype=torch.float32).pin_memory(),
+                 d_acts=torch.empty(T * K, dtype=torch.float32, device=dev),
+                 d_int=torch.empty(n_int, dtype=torch.int32, device=dev),
+                 d_grad=torch.empty(T * K, dtype=torch.float32, device=dev),
+                 d_out=torch.empty(2, dtype=torch.float32, device=dev),      # nll, skip (int32 bits)
+                 ws=torch.empty(max(lib.ctcb_ctc_workspace_bytes(1, T, L), 1), dtype=torch.uint8, device=dev))
+        _scratch[key] = b
+    return b
+
+
 def ctc_loss(params, seq, blank=0):
     """CTC loss function (reference signature).  params - n x m matrix of n-D probability
     distributions over m frames, Fortran order; seq - label ids.  Returns (objective, gradient with
-    respect to the unnormalised inputs, skip)."""
+    respect to the unnormalised inputs, skip).  Two H2D copies, one kernel, two D2H copies, ONE synchronisation."""
     _check_params(params)
     if seq is None:
         raise TypeError("Argument 'seq' must not be None")
@@ -68,15 +93,26 @@ def ctc_loss(params, seq, blank=0):
         raise ValueError("Buffer dtype mismatch, expected 'int' but got '%s'" % seq.dtype)
     torch = _ctcb.require_cuda()
     K, T = params.shape
+    L = int(seq.shape[0])
     dev = torch.device("cuda", torch.cuda.current_device())
+    b = _single_utterance_buffers(torch, dev, T, K, L)
     # K x T Fortran == T x K row-major: the frame-contiguous layout the kernel streams
-    acts = torch.from_numpy(np.ascontiguousarray(params.T, dtype=np.float32)).to(dev).view(1, T, K)
-    lab = torch.from_numpy(seq if seq.size else np.zeros(1, np.int32)).to(dev)
-    off = torch.tensor([0, seq.shape[0]], dtype=torch.int32, device=dev)
-    tl = torch.tensor([T], dtype=torch.int32, device=dev)
-    nll, grad, skip = ctc_loss_batch(acts, tl, lab, off, seq.shape[0], blank=blank, is_prob=True)
-    g = grad.view(T, K).cpu().numpy().astype(np.float64)
-    return float(nll.item()), np.asfortranarray(g.T), bool(skip.item())
+    b["h_acts"].numpy().reshape(T, K)[...] = params.T
+    hi = b["h_int"].numpy()
+    hi[0], hi[1], hi[2] = 0, L, T
+    hi[3:3 + L] = seq
+    b["d_acts"].copy_(b["h_acts"], non_blocking=True)
+    b["d_int"].copy_(b["h_int"], non_blocking=True)
+    d_int, d_out = b["d_int"], b["d_out"]
+    check(lib.ctcb_ctc_loss_grad_f32(ptr(b["d_acts"]), 1, T * K, K, d_int.data_ptr() + 12, d_int.data_ptr(),
+                                     d_int.data_ptr() + 8, 1, T, K, L, int(blank), ptr(b["d_grad"]), d_out.data_ptr(),
+                                     d_out.data_ptr() + 4, ptr(b["ws"]), b["ws"].numel(), _ctcb.current_stream()))
+    b["h_grad"].copy_(b["d_grad"], non_blocking=True)
+    b["h_out"].copy_(d_out, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    out = b["h_out"].numpy()
+    g = b["h_grad"].numpy().reshape(T, K).astype(np.float64)
+    return float(out[0]), np.asfortranarray(g.T), bool(out[1:2].view(np.int32)[0] != 0)
 
 
 def decode_best_path(probs, blank=0):

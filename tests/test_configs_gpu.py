@@ -43,6 +43,10 @@ CASES = {
     "c4_b2": dict(D=41, K=35, H=2048, N=5, tl=3, T=1500, L=150, B=2),
     # a ragged C3-shaped minibatch that is wider than one 16-utterance MMA tile of the tensor-core sweep
     "c3_ragged_b24": dict(D=41, K=32, H=1024, N=3, tl=2, T=160, L=20, B=24, ragged=True),
+    # the reference's REAL input widths are context windows of the 41 features: 41*15 = 615 (SWBD, swbd-utils/runSwbd.sh:20)
+    # and 41*23 = 943 (TIMIT, timit-utils/runTimit.sh:21) -- the first-layer contractions then run on the tensor cores
+    "swbd_input_d615_b4": dict(D=615, K=35, H=512, N=2, tl=1, T=120, L=20, B=4),
+    "timit_input_d943_b4": dict(D=943, K=62, H=512, N=2, tl=1, T=120, L=20, B=4),
 }
 
 
@@ -128,7 +132,7 @@ def test_full_net_at_baseline_config(name, cuda):
         if i <= N:
             given.append(_rel(db.reshape(-1), odb.reshape(-1)))
 
-    small = (name == "c2_as_benchmarked")
+    small = (name == "c2_as_benchmarked") or name.endswith("_b4")
     plain_tol = GRAD_TOL if small else 5e-3
     _record(name, dict(config=c, cost_rel_err_max=cost_err, forward_activation_rel_err_max=fwd_err,
                        grad_rel_err_given_gpu_activations_max=max(given), grad_rel_err_given_gpu_activations=given,
