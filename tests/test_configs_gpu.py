@@ -132,7 +132,7 @@ def test_full_net_at_baseline_config(name, cuda):
         if i <= N:
             given.append(_rel(db.reshape(-1), odb.reshape(-1)))
 
-    small = (name == "c2_as_benchmarked") or name.endswith("_b4")
+    small = (name == "c2_as_benchmarked")       # the one config whose plain comparison happens to see no mask flip
     plain_tol = GRAD_TOL if small else 5e-3
     _record(name, dict(config=c, cost_rel_err_max=cost_err, forward_activation_rel_err_max=fwd_err,
                        grad_rel_err_given_gpu_activations_max=max(given), grad_rel_err_given_gpu_activations=given,
