@@ -96,6 +96,10 @@ int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha,
                   float *C, int64_t ldc, const float *bias, int relu, const float *mask_src,
                   void *workspace, size_t ws_bytes, void *stream);
 
+/* Diagnostic (CTCB_GEMM_TRACE=1): SM clock stamps of CTA (0,0,0) of the last tensor-core GEMM, HOST buffer of 64 x 8
+ * uint64 = per k-block {TMA issued, tile landed, low halves written, MMA thread saw it, MMAs issued, -, -, -}. */
+int ctcb_debug_gemm_trace(unsigned long long *host_out);
+
 /* ---- BRNN (replaces nnets.brnnet.NNet, ctc_fast/nnets/brnnet.py:10-277) --------------------- */
 typedef struct ctcb_brnn_config {
     int32_t inputDim;      /* brnnet.py:10 */

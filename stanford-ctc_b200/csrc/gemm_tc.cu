@@ -37,6 +37,8 @@ constexpr int TC_BK = 32;   // 32 fp32 = 128 bytes = one swizzle span
 constexpr int TC_SPLIT_WARPS = 8;
 constexpr int TC_THREADS = 128 + 32 * TC_SPLIT_WARPS;
 
+static unsigned long long *g_gemm_trace = nullptr;     // CTCB_GEMM_TRACE: stamps of the LAST tensor-core GEMM launched
+
 struct GemmTcArgs {
     int M, N, K;
     float *C; int64_t ldc;
@@ -46,7 +48,13 @@ struct GemmTcArgs {
     int kb_per_split;    // k-blocks per gridDim.z slice
     int nmma;            // debug (CTCB_GEMM_MMAS): 3 = full 3xTF32, 1 = hi.hi only (plain TF32, for rate experiments)
     int a_mn, b_mn;      // operand is MN-major in memory (stored K x M / K x N): fed to the tensor cores as it lies
+    unsigned long long *trace;   // optional (CTCB_GEMM_TRACE): [64 k-blocks][8] SM clock stamps of CTA (0,0,0)
 };
+#define TC_STAMP(i, slot)                                                                                       \
+    do {                                                                                                        \
+        if (g.trace && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && (i) < 64)                       \
+            g.trace[(i) * 8 + (slot)] = (unsigned long long)clock64();                                          \
+    } while (0)
 
 // ---------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t tc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -191,6 +199,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t sa = tc_smem_u32(base + s * STAGE_BYTES), sb = sa + 2 * A_BYTES;
                 const int k = (kb0 + i) * TC_BK;
                 if (leader) {
+                    TC_STAMP(i, 0);
                     tc_mbar_expect_tx(full, A_BYTES + B_BYTES);
                     if (g.a_mn) {      // four boxes of {32 m, 32 k}
 #pragma unroll
@@ -224,6 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES + B_BYTES) : tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
                 const uint32_t eb = tc_smem_u32(&bars[STAGES + s]);
                 if (leader) {
+                    TC_STAMP(i, 3);
 #pragma unroll
                     for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
                         const uint64_t aa = (uint64_t)k8 * stepA, ab = (uint64_t)k8 * stepB;
@@ -235,6 +245,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tc_mma_tf32(tmem_d, dA + aa, dB + ab, idesc, (i > 0 || k8 > 0) ? 1u : 0u);
                         }
                     }
+                    TC_STAMP(i, 4);
                     tc_commit(eb);                                 // slot free once these MMAs have read it
                 }
                 __syncwarp();
@@ -258,6 +269,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
+                if (tid == 0) TC_STAMP(i, 1);
                 const float4 *hiA = reinterpret_cast<const float4 *>(base + s * STAGE_BYTES);
                 float4 *loA = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + A_BYTES);
                 const float4 *hiB = reinterpret_cast<const float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES);
@@ -274,6 +286,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");    // generic writes -> tensor-core (async) proxy
                 __syncwarp();
                 if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&ready[s])) : "memory");
+                if (tid == 0) TC_STAMP(i, 2);
             }
         }
         __syncwarp();
@@ -551,6 +564,15 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
         if (nmma_env < 0) { const char *e = getenv("CTCB_GEMM_MMAS"); nmma_env = e ? atoi(e) : 3; }
         g.nmma = nmma_env;
     }
+    g.trace = nullptr;
+    {
+        static int tr_env = -1;
+        if (tr_env < 0) tr_env = getenv("CTCB_GEMM_TRACE") ? 1 : 0;
+        if (tr_env) {
+            if (!g_gemm_trace) cudaMalloc(&g_gemm_trace, 64 * 8 * sizeof(unsigned long long));
+            g.trace = g_gemm_trace;
+        }
+    }
     g.kb_per_split = (nkb + splits - 1) / splits;
     splits = (nkb + g.kb_per_split - 1) / g.kb_per_split;
     g.partial = splits > 1 ? part : nullptr;
@@ -577,3 +599,11 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
 }
 
 }  // namespace ctcb
+
+// Diagnostic: the per-k-block clock stamps of CTA (0,0,0) of the last tensor-core GEMM (CTCB_GEMM_TRACE=1):
+// [64][8] = {TMA issued, tile landed, lo written, MMA thread saw it, MMAs issued}.  Returns 0 when tracing is off.
+extern "C" int ctcb_debug_gemm_trace(unsigned long long *host_out) {
+    if (!ctcb::g_gemm_trace || !host_out) return 0;
+    if (cudaMemcpy(host_out, ctcb::g_gemm_trace, 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return 64;
+}

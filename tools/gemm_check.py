@@ -40,3 +40,12 @@ for (M, N, K, ta, tb) in shapes:
     ms = e0.elapsed_time(e1) / 10
     print("M=%5d N=%4d K=%5d tA=%d tB=%d  rel=%.2e maxabs=%.2e  %.3f ms  %.1f TFLOP/s(fp32-equiv)  [%s]" % (
         M, N, K, ta, tb, err, mx, ms, 2.0 * M * N * K / ms / 1e9, os.environ.get("CTCB_GEMM", "tc")), flush=True)
+    if os.environ.get("CTCB_GEMM_TRACE"):
+        import ctypes
+        buf = (ctypes.c_uint64 * 512)()
+        if lib.ctcb_debug_gemm_trace(buf):
+            tr = np.frombuffer(buf, dtype=np.uint64).reshape(64, 8).astype(np.int64)
+            t0 = tr[0, 0]
+            print("   k-block:  TMA issued   landed  lo written  MMA saw   MMAs issued   (SM cycles from the first TMA issue)")
+            for i in list(range(0, 8)) + [16, 17, 18, 19]:
+                print("   %6d  %11d %8d %11d %8d %13d" % ((i,) + tuple(int(tr[i, j] - t0) for j in range(5))))
