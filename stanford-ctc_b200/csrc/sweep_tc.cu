@@ -53,6 +53,7 @@ struct SweepTcArgs {
     uint32_t stage_bytes;     // 2 * STC_A_BYTES + 2 * Npad * 128
     uint32_t tmem_cols;
     int partial_own;          // 1: the partial product has its own shared-memory region (W prefetch across steps)
+    int wfence;               // experiment: writer-side proxy fence before the counter arrival
     int rotate;               // experiment (CTCB_SWEEP_TC_ROTATE=1): M-tile CTAs walk the k-blocks in rotated orders; measured: no effect
     int nomma;                // experiment (CTCB_SWEEP_TC_NOMMA=1): issue no MMA -- how fast does the operand stream alone run?
     int resident;             // 1: this CTA's W slice never leaves the SM: hi half in TENSOR MEMORY (A operand of the
@@ -494,7 +495,11 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             __syncthreads();
             if (tid == 0) {
                 STC_STAMP(9);
-                asm volatile("fence.proxy.async;" ::: "memory");
+                // release: the CTA's state stores (ordered before this thread by the barrier above) become visible at
+                // device scope before the count does.  The generic->async proxy fence belongs to the READER (after its
+                // acquire, before its TMA loads); a second one here only cost ~500 cycles per step (CTCB_SWEEP_TC_WFENCE=1
+                // brings it back).
+                if (a.wfence) asm volatile("fence.proxy.async;" ::: "memory");
                 asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ctr), "r"(1u) : "memory");
                 STC_STAMP(10);
             }
@@ -697,6 +702,7 @@ int run_sweep_tc(int mode, int T, int B, int H, const int32_t *Tlen, const float
     a.ndir = ndir; a.MT = H / STC_BM; a.NS = p.NS; a.Npad = p.Npad; a.nkb = H / STC_CS / STC_BK;
     a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.tmem_cols = (uint32_t)p.tmem_cols; a.partial_own = p.partial_own;
     a.resident = p.resident;
+    { static int wf = -1; if (wf < 0) { const char *e = getenv("CTCB_SWEEP_TC_WFENCE"); wf = e ? atoi(e) : 0; } a.wfence = wf; }
     { static int ro = -1; if (ro < 0) { const char *e = getenv("CTCB_SWEEP_TC_ROTATE"); ro = e ? atoi(e) : 0; } a.rotate = ro; }
     { static int nm = -1; if (nm < 0) { const char *e = getenv("CTCB_SWEEP_TC_NOMMA"); nm = e ? atoi(e) : 0; } a.nomma = nm; }
     a.whi[0] = stack; a.whi[1] = stack + (size_t)(ndir - 1) * 2 * H * H;
