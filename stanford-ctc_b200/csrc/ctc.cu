@@ -567,6 +567,116 @@ __global__ void __launch_bounds__(64) ctc_pair_kernel(CtcArgs a) {
     }
 }
 
+// Gradient of one time tile from the spilled trellis: alpha-tilde (plane A) and the beta pre-emission sums (plane B) of
+// every frame are in the workspace, so the frames are independent -- any warp can take any tile.
+template <int P>
+__device__ __forceinline__ void combine_tile(const CtcArgs &a, const WarpCtx &c, const LaneLabels<P> &q, int tile, bool recur,
+                                             const double *wsA, const double *wsB) {
+    constexpr int LP = 64 * P;
+    const int lane = c.lane, T = c.T, t0 = tile * TT;
+    float *te = c.te0;
+    issue_tile(a, c.base, t0, T, te, lane);
+    cp_async_wait<0>();
+    __syncwarp();
+    const float Z = tile_stats(a, t0, T, te, lane);
+    unsigned *tgu = reinterpret_cast<unsigned *>(c.tg);
+    for (int idx = lane; idx < TT * a.Kp; idx += 32) tgu[idx] = 0u;
+    __syncwarp();
+    const int rmax = min(TT, T - t0);
+    if (recur) {
+        for (int r = 0; r < rmax; ++r) {
+            const int t = t0 + r;
+            const double2 *arow = reinterpret_cast<const double2 *>(wsA + (int64_t)t * LP) + lane * P;
+            const double2 *prow = reinterpret_cast<const double2 *>(wsB + (int64_t)t * LP) + lane * P;
+            double xb[P], xl[P], pb[P], pll[P];
+#pragma unroll
+            for (int j = 0; j < P; ++j) {
+                const double2 av = arow[j], pv = prow[j];
+                xb[j] = av.x; xl[j] = av.y; pb[j] = pv.x; pll[j] = pv.y;
+            }
+            occupancy_frame<P>(q, a.blank, lane, xb, xl, pb, pll, tgu + r * a.Kp);
+        }
+    }
+    __syncwarp();
+    tile_epilogue(a, c, t0, rmax, te, tgu, 1.f / Z);
+}
+
+// Latency shape, round 2 (a training step's minibatch: at most one utterance per SM): the serial chain carries ONLY the
+// recurrences.  Warp 0 runs alpha forward over all frames and warp 1 beta backward over all frames, at the same time,
+// each spilling its scaled states (two workspace planes); then the frames are independent and ALL warps of the CTA turn
+// the two planes into occupancies and the gradient, one time tile each.  Against the meet-in-the-middle kernel above
+// (which computes occupancies and gradient on the two serial warps) the chain loses ~40 % of its instructions:
+// 0.153 -> 0.1 ms for the 32 utterances of the C2 step.
+template <int P>
+__global__ void __launch_bounds__(256) ctc_par_kernel(CtcArgs a, int NW) {
+    extern __shared__ float smem[];
+    __shared__ int fail_flag, S_s;
+    __shared__ float lz_s;
+    __shared__ double fin_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int u = blockIdx.x;
+    WarpCtx c;
+    c.lane = lane;
+    c.T = min(a.Tlen[u], a.Tmax);
+    c.ntiles = (c.T + TT - 1) / TT;
+    c.base = a.acts + (int64_t)u * a.us;
+    c.gbase = a.grad + (int64_t)u * a.us;
+    double *wsA = reinterpret_cast<double *>(a.ws) + (int64_t)u * 2 * a.ws_utt;
+    double *wsB = wsA + a.ws_utt;
+    const int lo = a.loff[u];
+    LaneLabels<P> q;
+    q.load(a, lo, a.loff[u + 1] - lo, lane);
+    const bool short_utt = (c.T < q.nlab);
+    const bool recur = !short_utt && c.T > 0;
+    if (threadIdx.x == 0) { fail_flag = (c.T <= 0) ? 1 : 0; S_s = 0; lz_s = 0.f; fin_s = 1.0; }
+    __syncthreads();
+    const size_t tile_f = (size_t)TT * a.Kp;
+    if (warp < 2) {
+        // ---- phase 1: the two recurrences, nothing else on the chain
+        c.nbuf = 2;
+        c.te0 = smem + (size_t)warp * 2 * tile_f;
+        c.tg = nullptr;
+        c.wsu = (warp == 0) ? wsA : wsB;
+        double x0[P], x1[P];
+#pragma unroll
+        for (int j = 0; j < P; ++j) x0[j] = x1[j] = 0.0;
+        int kscale = 0, S = 0;
+        float logZ = 0.f;
+        bool ok = true;
+        if (warp == 0) {
+            if (lane == 0) x0[0] = 1.0;
+            ok = alpha_tiles<P, false>(a, c, q, 0, c.ntiles, recur, x0, x1, kscale, S, logZ);
+            double final_sum = 1.0;
+            if (ok && recur) {
+                final_sum = final_mass<P>(q, lane, c.T, x0, x1);
+                if (!(final_sum > 0.0)) ok = false;
+            }
+            const float lz = warp_sum(logZ);
+            if (lane == 0) { lz_s = lz; fin_s = final_sum; S_s = S; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < P; ++j)
+                if (lane * P + j == q.nlab) x0[j] = 1.0;
+            if (recur) ok = beta_tiles<P, false>(a, c, q, c.ntiles - 1, 0, true, x0, x1, kscale);
+        }
+        if (!ok && lane == 0) fail_flag = 1;
+    }
+    __threadfence_block();
+    __syncthreads();                       // both planes of the trellis are in the workspace
+    // ---- phase 2: frames are independent now -- every warp takes time tiles
+    if (!fail_flag && warp < NW) {
+        c.nbuf = 1;
+        c.te0 = smem + (size_t)warp * 2 * tile_f;
+        c.tg = c.te0 + tile_f;
+        for (int tile = warp; tile < c.ntiles; tile += NW) combine_tile<P>(a, c, q, tile, recur, wsA, wsB);
+    }
+    __syncthreads();
+    const bool fail = fail_flag != 0;
+    if (fail) zero_rows(a, c.gbase, 0, c.T, threadIdx.x, blockDim.x);
+    zero_rows(a, c.gbase, max(c.T, 0), a.Tmax, threadIdx.x, blockDim.x);
+    if (threadIdx.x == 0) write_loss(a, u, short_utt, fail, fin_s, S_s, lz_s);
+}
+
 // -------------------------------------------------------------------------------------------
 // best path: per-frame argmax + collapse (ctc_fast.pyx:154-187).  One warp per utterance.
 // -------------------------------------------------------------------------------------------
@@ -620,7 +730,8 @@ using namespace ctcb;
 extern "C" size_t ctcb_ctc_workspace_bytes(int B, int Tmax, int max_labels) {
     const int P = pairs_per_lane(max_labels);
     if (P == 0 || B <= 0 || Tmax <= 0) return 0;
-    return (size_t)B * (size_t)Tmax * (size_t)(64 * P) * sizeof(double);
+    // small batches take the three-phase latency kernel, which spills alpha AND beta for every frame (two planes)
+    return (size_t)B * (size_t)Tmax * (size_t)(64 * P) * sizeof(double) * (B <= 256 ? 2 : 1);
 }
 
 extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t utt_stride, int64_t frame_stride,
@@ -656,7 +767,33 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     // few utterances (a training step): two warps per utterance meet in the middle of the trellis, one CTA each;
     // CTCB_CTC=warp|pair forces a shape (tests)
     static int shape_env = -1;
-    if (shape_env < 0) { const char *e = getenv("CTCB_CTC"); shape_env = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'p' ? 2 : 0)); }
+    if (shape_env < 0) {
+        const char *e = getenv("CTCB_CTC");
+        shape_env = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'p' && e[1] == 'a' && e[2] == 'r' ? 3 : (e[0] == 'p' ? 2 : 0)));
+    }
+    {   // at most one utterance per SM (a training step): recurrences on two warps, gradient on all eight
+        const size_t tile_b = (size_t)TT * a.Kp * sizeof(float);
+        int NW = 8;
+        while (NW > 2 && (size_t)2 * NW * tile_b > 160 * 1024) NW >>= 1;
+        const size_t smem = (size_t)2 * NW * tile_b;
+        const bool par = (shape_env == 3 && B <= 256) || (shape_env == 0 && B <= num_sms());
+        if (par && smem <= 200 * 1024) {
+            a.nbuf = 2;
+#define LAUNCH_PAR(PP)                                                                                 \
+    case PP: {                                                                                         \
+        CTCB_CUDA_CHECK(cudaFuncSetAttribute(ctc_par_kernel<PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        ctc_par_kernel<PP><<<B, 256, smem, st>>>(a, NW);                                               \
+        break;                                                                                         \
+    }
+            switch (P) {
+                LAUNCH_PAR(1) LAUNCH_PAR(2) LAUNCH_PAR(4) LAUNCH_PAR(8) LAUNCH_PAR(16)
+                default: return set_error(CTCB_EINVAL, "bad P");
+            }
+#undef LAUNCH_PAR
+            CTCB_LAUNCH_CHECK();
+            return CTCB_OK;
+        }
+    }
     // the two-warp shape wins as long as its CTAs (one per utterance) fit the SMs in one wave: below that the
     // one-warp shape leaves the schedulers short of warps (C5 sweep: 1.6 vs 3.1 ms at T=2000, B=292 vs 604)
     const size_t smem_pair = (size_t)2 * 3 * TT * a.Kp * sizeof(float);

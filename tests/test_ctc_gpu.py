@@ -167,18 +167,20 @@ def test_best_path_matches_reference_semantics(cuda):
     assert ctc_fast.decode_best_path(np.asfortranarray(q)) == ([3, 3, 5], [2, 4, 7])
 
 
-def test_one_warp_shape_when_forced(cuda):
-    """Small batches take the two-warp meet-in-the-middle kernel; CTCB_CTC=warp forces the one-warp-per-utterance
-    kernel (the throughput shape of large batches) through the same golden / edge cases."""
+@pytest.mark.parametrize("shape", ["warp", "pair"])
+def test_other_kernel_shapes_when_forced(shape, cuda):
+    """Small batches take the three-phase latency kernel (recurrences on two warps, gradient on all warps); CTCB_CTC=warp
+    forces the one-warp-per-utterance kernel (the throughput shape of large batches), CTCB_CTC=pair the two-warp
+    meet-in-the-middle kernel (mid-sized batches), through the same golden / edge cases."""
     import os
     import subprocess
     import sys
     here = os.path.dirname(os.path.abspath(__file__))
     root = os.path.dirname(here)
     code = ("import os,sys; sys.path[:0]=[%r,%r,%r]; import pytest; "
-            "sys.exit(pytest.main(['-q','-p','no:cacheprovider','-k','golden_cases or ragged_batch or pairs_per_lane or fused_softmax', %r]))"
+            "sys.exit(pytest.main(['-q','-p','no:cacheprovider','-k','golden_cases or ragged_batch or pairs_per_lane or fused_softmax or tile_boundaries', %r]))"
             % (root, os.path.join(root, "stanford-ctc_b200"), here, os.path.abspath(__file__)))
-    env = dict(os.environ, CTCB_CTC="warp")
+    env = dict(os.environ, CTCB_CTC=shape)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
 
