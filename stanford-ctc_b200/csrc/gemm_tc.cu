@@ -48,6 +48,10 @@ struct GemmTcArgs {
     int kb_per_split;    // k-blocks per gridDim.z slice
     int nmma;            // debug (CTCB_GEMM_MMAS): 3 = full 3xTF32, 1 = hi.hi only (plain TF32, for rate experiments)
     int a_mn, b_mn;      // operand is MN-major in memory (stored K x M / K x N): fed to the tensor cores as it lies
+    int ts;              // 1: the A tile goes to the tensor cores THROUGH TENSOR MEMORY: four splitter warps read each row of
+                         //    the landed tile once and tcgen05.st its value and its low half next to the accumulator; the MMAs
+                         //    take A from there (.ts form).  Shared-memory traffic per k-block of a 256-wide tile falls from
+                         //    288 KB (the bound the round-2 trace showed, profiles/gemm_tc_trace_r2.txt) to 224 KB.
     unsigned long long *trace;   // optional (CTCB_GEMM_TRACE): [64 k-blocks][8] SM clock stamps of CTA (0,0,0)
 };
 #define TC_STAMP(i, slot)                                                                                       \
@@ -91,6 +95,24 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 consecutive columns of the calling thread's tensor-memory lane
+__device__ __forceinline__ void tc_tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -180,7 +202,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(g.ts ? 512u : (uint32_t)BN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -220,6 +242,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ------------------------------------------------------------ MMA issuer (whole warp, elected issue)
             const bool leader = tc_elect_one();
             const uint32_t idesc = tc_idesc(TC_BM, BN, g.a_mn, g.b_mn);
+            const uint32_t idesc_ts = tc_idesc(TC_BM, BN, 0, g.b_mn);     // A from tensor memory: rows = lanes, k = columns
             // per k-step (8 floats of K): 32 bytes along the swizzled row (K-major) or one whole 1 KB atom (MN-major)
             const uint64_t stepA = (uint64_t)((g.a_mn ? 1024 : 32) >> 4), stepB = (uint64_t)((g.b_mn ? 1024 : 32) >> 4);
             for (int i = 0; i < nkb; ++i) {
@@ -232,7 +255,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint64_t dB = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES) : tc_smem_desc(a + 2 * A_BYTES);
                 const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES + B_BYTES) : tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
                 const uint32_t eb = tc_smem_u32(&bars[STAGES + s]);
-                if (leader) {
+                if (g.ts) tc_fence_after();     // the splitters' tensor-memory stores of this stage
+                if (leader && g.ts) {
+                    TC_STAMP(i, 3);
+                    const uint32_t ta = tmem_d + (uint32_t)BN + (uint32_t)(64 * s);      // value at +0, low half at +32
+#pragma unroll
+                    for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
+                        const uint64_t ab = (uint64_t)k8 * stepB;
+                        tc_mma_tf32_ts(tmem_d, ta + 32 + 8 * k8, dB + ab, idesc_ts, (i > 0 || k8 > 0) ? 1u : 0u);   // lo . hi
+                        tc_mma_tf32_ts(tmem_d, ta + 8 * k8, dBl + ab, idesc_ts, 1u);                                // hi . lo
+                        tc_mma_tf32_ts(tmem_d, ta + 8 * k8, dB + ab, idesc_ts, 1u);                                 // hi . hi
+                    }
+                    TC_STAMP(i, 4);
+                    tc_commit(eb);
+                } else if (leader) {
                     TC_STAMP(i, 3);
 #pragma unroll
                     for (int k8 = 0; k8 < TC_BK / 8; ++k8) {
@@ -266,6 +302,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
                 return r;
             };
+            if (g.ts) {
+                // warps 4..7: the A tile, row by row, into tensor memory (warp w owns lanes 32 (w % 4) ..); warps 8..11: B's low half
+                const bool a_warp = (warp < 8);
+                const int q = warp & 3, row = 32 * q + lane;
+                const int tb = threadIdx.x - 256;                     // 0..127 within the B warps
+                constexpr int NB2 = (int)(B_BYTES / 16) / 128;
+                for (int i = 0; i < nkb; ++i) {
+                    const int s = i % STAGES, use = i / STAGES;
+                    tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
+                    if (tid == 0) TC_STAMP(i, 1);
+                    const uint8_t *sA = base + s * STAGE_BYTES;
+                    if (a_warp) {
+                        uint32_t r[32];
+                        if (g.a_mn) {     // boxes of {32 m, 32 k}: box q holds this warp's rows; 32-byte chunks XOR-ed with k % 4
+#pragma unroll
+                            for (int k = 0; k < 32; ++k)
+                                r[k] = *reinterpret_cast<const uint32_t *>(sA + q * 4096 + k * 128 + ((((lane >> 3) ^ (k & 3)) << 5) | ((lane & 7) << 2)));
+                        } else {          // K-major rows of 128 bytes, 16-byte chunks XOR-ed with row % 8
+#pragma unroll
+                            for (int c = 0; c < 8; ++c) {
+                                const uint4 v = *reinterpret_cast<const uint4 *>(sA + row * 128 + ((c ^ (row & 7)) << 4));
+                                r[4 * c] = v.x; r[4 * c + 1] = v.y; r[4 * c + 2] = v.z; r[4 * c + 3] = v.w;
+                            }
+                        }
+                        const uint32_t ta = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)BN + (uint32_t)(64 * s);
+                        tc_tmem_st32(ta, r);
+#pragma unroll
+                        for (int k = 0; k < 32; ++k) {
+                            const float x = __uint_as_float(r[k]);
+                            r[k] = __float_as_uint(x - __uint_as_float(r[k] & 0xffffe000u));
+                        }
+                        tc_tmem_st32(ta + 32, r);
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                    } else {
+                        const float4 *hiB = reinterpret_cast<const float4 *>(sA + 2 * A_BYTES);
+                        float4 *loB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES);
+                        float4 vb[NB2];
+#pragma unroll
+                        for (int j = 0; j < NB2; ++j) vb[j] = hiB[tb + j * 128];
+#pragma unroll
+                        for (int j = 0; j < NB2; ++j) loB[tb + j * 128] = lo4(vb[j]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc_smem_u32(&ready[s])) : "memory");
+                    if (tid == 0) TC_STAMP(i, 2);
+                }
+            } else
             for (int i = 0; i < nkb; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
@@ -337,7 +422,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(g.ts ? 512u : (uint32_t)BN) : "memory");
     }
 }
 
@@ -558,6 +643,11 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     const int nkb = (K + TC_BK - 1) / TC_BK;
     GemmTcArgs g;
     g.a_mn = a_mn; g.b_mn = b_mn;
+    {
+        static int ts_env = -1;     // CTCB_GEMM_TS=0: both operands from shared memory (the round-1 form)
+        if (ts_env < 0) { const char *e = getenv("CTCB_GEMM_TS"); ts_env = e ? atoi(e) : 1; }
+        g.ts = ts_env;
+    }
     g.M = M; g.N = N; g.K = K; g.C = C; g.ldc = ldc; g.alpha = alpha; g.beta = beta; g.bias = bias; g.relu = relu; g.mask = mask_src;
     {
         static int nmma_env = -1;
@@ -583,7 +673,7 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     if ((rc = b_mn ? make_map_mn(&tB, Buse, N, K, ldb_use) : make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
     static int stages_env = -1;   // CTCB_GEMM_STAGES=2 with BN=64: 96 KB/CTA -> two CTAs per SM overlap prologue/epilogue
     if (stages_env < 0) { const char *e = getenv("CTCB_GEMM_STAGES"); stages_env = e ? atoi(e) : 0; }
-    if (BN == 64 && stages_env == 2) rc = launch_tc<64, 2>(tA, tB, g, splits, st);
+    if (BN == 64 && stages_env == 2) { g.ts = 0; rc = launch_tc<64, 2>(tA, tB, g, splits, st); }   // two CTAs per SM: no room for 512 columns each
     else if (BN == 64) rc = launch_tc<64, 4>(tA, tB, g, splits, st);
     else if (BN == 256) rc = launch_tc<256, 2>(tA, tB, g, splits, st);
     else rc = launch_tc<128, 3>(tA, tB, g, splits, st);
