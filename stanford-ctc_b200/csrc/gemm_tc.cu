@@ -172,11 +172,17 @@ __device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int
     return v;
 }
 
-template <int BN, int STAGES>
+// TS = true: the A tile reaches the tensor cores through tensor memory, so a stage holds A once and B twice (value + low
+// half); TS = false: both operands from shared memory, A and B twice each.
+template <int BN, int STAGES, bool TS>
 __global__ void __launch_bounds__(TC_THREADS)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
     constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
-    constexpr uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    constexpr uint32_t B_OFF = TS ? A_BYTES : 2 * A_BYTES;                 // where B's value tile sits inside a stage
+    constexpr uint32_t STAGE_BYTES = B_OFF + 2 * B_BYTES;
+    // tensor-memory columns: the accumulator, then per stage 32 + 32 columns for the A tile (power of two)
+    constexpr uint32_t TMEM_COLS = !TS ? (uint32_t)BN : ((BN + 64 * STAGES) <= 128 ? 128u : ((BN + 64 * STAGES) <= 256 ? 256u : 512u));
+    static_assert(!TS || BN + 64 * STAGES <= 512, "accumulator + A stages exceed the tensor memory");
     extern __shared__ __align__(1024) uint8_t tc_smem[];
     // 1024-byte alignment is required by SWIZZLE_128B: align manually (dynamic smem base is only 16B-aligned by contract)
     uint8_t *base = (uint8_t *)(((uintptr_t)tc_smem + 1023) & ~(uintptr_t)1023);
@@ -202,7 +208,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {   // TMEM: BN fp32 accumulator columns (power of two >= 32)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(g.ts ? 512u : (uint32_t)BN) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc_smem_u32(tmem_slot)), "r"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
@@ -218,7 +224,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int s = i % STAGES, use = i / STAGES;
                 if (use > 0) tc_mbar_wait(tc_smem_u32(&bars[STAGES + s]), (uint32_t)((use - 1) & 1));
                 const uint32_t full = tc_smem_u32(&bars[s]);
-                const uint32_t sa = tc_smem_u32(base + s * STAGE_BYTES), sb = sa + 2 * A_BYTES;
+                const uint32_t sa = tc_smem_u32(base + s * STAGE_BYTES), sb = sa + B_OFF;
                 const int k = (kb0 + i) * TC_BK;
                 if (leader) {
                     TC_STAMP(i, 0);
@@ -252,11 +258,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t a = tc_smem_u32(base + s * STAGE_BYTES);
                 const uint64_t dA = g.a_mn ? tc_smem_desc_mn(a) : tc_smem_desc(a);
                 const uint64_t dAl = g.a_mn ? tc_smem_desc_mn(a + A_BYTES) : tc_smem_desc(a + A_BYTES);
-                const uint64_t dB = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES) : tc_smem_desc(a + 2 * A_BYTES);
-                const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + 2 * A_BYTES + B_BYTES) : tc_smem_desc(a + 2 * A_BYTES + B_BYTES);
+                const uint64_t dB = g.b_mn ? tc_smem_desc_mn(a + B_OFF) : tc_smem_desc(a + B_OFF);
+                const uint64_t dBl = g.b_mn ? tc_smem_desc_mn(a + B_OFF + B_BYTES) : tc_smem_desc(a + B_OFF + B_BYTES);
                 const uint32_t eb = tc_smem_u32(&bars[STAGES + s]);
-                if (g.ts) tc_fence_after();     // the splitters' tensor-memory stores of this stage
-                if (leader && g.ts) {
+                if (TS) tc_fence_after();       // the splitters' tensor-memory stores of this stage
+                if (leader && TS) {
                     TC_STAMP(i, 3);
                     const uint32_t ta = tmem_d + (uint32_t)BN + (uint32_t)(64 * s);      // value at +0, low half at +32
 #pragma unroll
@@ -302,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 r.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
                 return r;
             };
-            if (g.ts) {
+            if (TS) {
                 // warps 4..7: the A tile, row by row, into tensor memory (warp w owns lanes 32 (w % 4) ..); warps 8..11: B's low half
                 const bool a_warp = (warp < 8);
                 const int q = warp & 3, row = 32 * q + lane;
@@ -337,8 +343,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                         tc_fence_before();
                     } else {
-                        const float4 *hiB = reinterpret_cast<const float4 *>(sA + 2 * A_BYTES);
-                        float4 *loB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + 2 * A_BYTES + B_BYTES);
+                        const float4 *hiB = reinterpret_cast<const float4 *>(sA + B_OFF);
+                        float4 *loB = reinterpret_cast<float4 *>(base + s * STAGE_BYTES + B_OFF + B_BYTES);
                         float4 vb[NB2];
 #pragma unroll
                         for (int j = 0; j < NB2; ++j) vb[j] = hiB[tb + j * 128];
@@ -351,7 +357,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (tid == 0) TC_STAMP(i, 2);
                 }
             } else
-            for (int i = 0; i < nkb; ++i) {
+            for (int i = 0; i < nkb && !TS; ++i) {
                 const int s = i % STAGES, use = i / STAGES;
                 tc_mbar_wait(tc_smem_u32(&bars[s]), (uint32_t)(use & 1));       // TMA bytes have landed
                 if (tid == 0) TC_STAMP(i, 1);
@@ -422,7 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(g.ts ? 512u : (uint32_t)BN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TMEM_COLS) : "memory");
     }
 }
 
@@ -580,12 +586,12 @@ size_t gemm_tc_workspace_bytes(int M, int N, int K) {
     return align_up(prep, 256) + align_up(part, 256) + 1024;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TS>
 static int launch_tc(const CUtensorMap &tA, const CUtensorMap &tB, const GemmTcArgs &g, int splits, cudaStream_t st) {
-    constexpr size_t smem = (size_t)STAGES * (2 * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (3 * STAGES + 1) * 8 + 16 + 1024;
-    CTCB_CUDA_CHECK(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    constexpr size_t smem = (size_t)STAGES * ((TS ? 1 : 2) * TC_BM * TC_BK * 4 + 2 * BN * TC_BK * 4) + (3 * STAGES + 1) * 8 + 16 + 1024;
+    CTCB_CUDA_CHECK(cudaFuncSetAttribute((gemm_tc_kernel<BN, STAGES, TS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 grid((g.N + BN - 1) / BN, (g.M + TC_BM - 1) / TC_BM, splits);
-    gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, smem, st>>>(tA, tB, g);
+    gemm_tc_kernel<BN, STAGES, TS><<<grid, TC_THREADS, smem, st>>>(tA, tB, g);
     CTCB_LAUNCH_CHECK();
     return CTCB_OK;
 }
@@ -673,10 +679,19 @@ int run_gemm_tc(int transA, int transB, int M, int N, int K, float alpha, const 
     if ((rc = b_mn ? make_map_mn(&tB, Buse, N, K, ldb_use) : make_map(&tB, Buse, N, K, ldb_use, BN)) != CTCB_OK) return rc;
     static int stages_env = -1;   // CTCB_GEMM_STAGES=2 with BN=64: 96 KB/CTA -> two CTAs per SM overlap prologue/epilogue
     if (stages_env < 0) { const char *e = getenv("CTCB_GEMM_STAGES"); stages_env = e ? atoi(e) : 0; }
-    if (BN == 64 && stages_env == 2) { g.ts = 0; rc = launch_tc<64, 2>(tA, tB, g, splits, st); }   // two CTAs per SM: no room for 512 columns each
-    else if (BN == 64) rc = launch_tc<64, 4>(tA, tB, g, splits, st);
-    else if (BN == 256) rc = launch_tc<256, 2>(tA, tB, g, splits, st);
-    else rc = launch_tc<128, 3>(tA, tB, g, splits, st);
+    // Tile shapes.  TS (default): 256-wide, 2 stages of 80 KB, one CTA per SM; 128-wide with 2 stages of 48 KB so that TWO
+    // CTAs share an SM (2 x 256 tensor-memory columns) and one's epilogue runs under the other's main loop; 64-wide, 4 stages.
+    if (!g.ts) {
+        if (BN == 64 && stages_env == 2) rc = launch_tc<64, 2, false>(tA, tB, g, splits, st);
+        else if (BN == 64) rc = launch_tc<64, 4, false>(tA, tB, g, splits, st);
+        else if (BN == 256) rc = launch_tc<256, 2, false>(tA, tB, g, splits, st);
+        else rc = launch_tc<128, 3, false>(tA, tB, g, splits, st);
+    } else {
+        if (BN == 64) rc = launch_tc<64, 4, true>(tA, tB, g, splits, st);
+        else if (BN == 256) rc = launch_tc<256, 2, true>(tA, tB, g, splits, st);
+        else if (stages_env == 3) rc = launch_tc<128, 3, true>(tA, tB, g, splits, st);
+        else rc = launch_tc<128, 2, true>(tA, tB, g, splits, st);
+    }
     if (rc != CTCB_OK) return rc;
     if (splits > 1) {
         const int64_t total = (int64_t)M * N;
