@@ -175,7 +175,7 @@ __device__ __forceinline__ float tc_epilogue(const GemmTcArgs &g, float acc, int
 // TS = true: the A tile reaches the tensor cores through tensor memory, so a stage holds A once and B twice (value + low
 // half); TS = false: both operands from shared memory, A and B twice each.
 template <int BN, int STAGES, bool TS>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, (TS && BN == 128 && STAGES == 2) ? 2 : 1)     // 128-wide: two CTAs per SM
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, GemmTcArgs g) {
     constexpr uint32_t A_BYTES = TC_BM * TC_BK * 4, B_BYTES = BN * TC_BK * 4;
     constexpr uint32_t B_OFF = TS ? A_BYTES : 2 * A_BYTES;                 // where B's value tile sits inside a stage
