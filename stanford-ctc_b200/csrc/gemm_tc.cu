@@ -532,7 +532,14 @@ static int tc_pick_bn(int M, int N, int K) {
     if (force < 0) { const char *e = getenv("CTCB_GEMM_BN"); force = e ? atoi(e) : 0; }
     if (force == 64 || force == 128 || force == 256) return force;
     if (N <= 64) return 64;
-    // measured (tools/gemm_rate.py): 256-wide tiles win once they still fill >= 2 waves of CTAs (16384x2048x2048:
+    {   // A through tensor memory (default): the 128-wide tile runs two CTAs per SM -- one's epilogue and pipeline fill under
+        // the other's main loop -- and beats the 256-wide one everywhere (48000x2048x2048: 228 vs 185 TFLOP/s; 25600x1024x1024:
+        // 172 vs 136; weight gradients 2048x2048x192000: 205 vs 203)
+        static int ts_env = -1;
+        if (ts_env < 0) { const char *e = getenv("CTCB_GEMM_TS"); ts_env = e ? atoi(e) : 1; }
+        if (ts_env) return 128;
+    }
+    // both operands from shared memory (CTCB_GEMM_TS=0), measured in round 1: 256-wide tiles win once they still fill >= 2 waves of CTAs (16384x2048x2048:
     // 192 vs 163 TFLOP/s fp32-equivalent) and lose on small problems (6400x512x512: 0.062 vs 0.048 ms)
     if (N >= 256 && (int64_t)((M + TC_BM - 1) / TC_BM) * ((N + 255) / 256) >= 2 * num_sms()) return 256;
     // reduction-heavy shapes (the weight gradients: 512 x 512 outputs over K = T*B rows) are split over K anyway;
