@@ -8,21 +8,22 @@
 // and a product is three MMAs accumulated in fp32 in tensor memory:  lo.hi + hi.lo + hi.hi
 // (the dropped lo.lo term is ~2^-20 relative) -- "3xTF32", ~1e-6 relative error per product.
 //
-// Kernel shape: C[M x N] = A[M x K] . B[N x K]^T, both operands K-major.  One CTA (4 warps) per
-// 128 x BN output tile and K split (gridDim.z):
-//   warp 0 / lane 0 : TMA producer -- per k-block of 32 floats two 128B-swizzled tiles (A, B) into a
-//                     STAGES-deep shared-memory ring, mbarrier complete_tx;
-//   warps 4..7      : splitter -- as soon as a stage has landed, compute the lo tiles IN SHARED MEMORY
-//                     (lo = x - trunc_tf32(x) is element-wise, so it is oblivious to the 128B swizzle);
-//                     fence.proxy.async + mbarrier hand the stage to the MMA warp.  The kernel was bound by
-//                     the L2->SM fill (64 KB per k-block at ~42 B/cycle/SM, ncu: tensor pipe 31 %): producing
-//                     lo on chip halves that traffic and removes the lo arrays from HBM;
-//   warp 1 / lane 0 : MMA issuer  -- 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per k-block,
-//                     tcgen05.commit releases the ring slot; the last commit signals the epilogue;
-//   warps 0..3      : epilogue -- tcgen05.ld 32 lanes x 32 columns per warp, fused alpha/beta/bias/ReLU/
-//                     mask (or split-K partial), row stores.
-// Transposed operands and operands whose row pitch is not a multiple of 16 bytes are re-laid-out by a
-// prep kernel, so the tensor-core kernel only ever sees K-major tiles.
+// Kernel shape: C[M x N] = A[M x K] . B[N x K]^T.  One CTA (12 warps) per 128 x BN output tile and K split (gridDim.z):
+//   warp 0          : TMA producer -- per k-block of 32 floats the A and B tiles into a STAGES-deep shared-memory ring
+//                     (one box per K-major operand, boxes of {32 m, 32 k} for an MN-major one), mbarrier complete_tx;
+//   warps 4..7      : A splitters -- read each row of the landed A tile once and tcgen05.st its value and its low half
+//                     (lo = x - trunc_tf32(x)) into TENSOR MEMORY next to the accumulator;
+//   warps 8..11     : B splitters -- write B's low half in shared memory (element-wise, oblivious to the swizzle);
+//   warp 1          : MMA issuer  -- 4 k-steps x 3 tcgen05.mma.kind::tf32 (M=128, N=BN, K=8) per k-block, A from tensor
+//                     memory (.ts form), B by shared-memory descriptor; tcgen05.commit releases the ring slot;
+//   warps 0..3      : epilogue -- tcgen05.ld 32 lanes x 32 columns per warp, fused alpha/beta/bias/ReLU/mask (or split-K
+//                     partial), row stores.
+//   Producer and MMA warps run warp-uniform and issue from the elect.sync lane (see tc_elect_one).
+// The default tile is 128 wide with two CTAs per SM (2 x 256 tensor-memory columns, 2 x 96 KB of shared memory), so one
+// CTA's epilogue and pipeline fill run under the other's main loop.  CTCB_GEMM_TS=0 selects the round-1 form (both
+// operands and both low halves in shared memory, eight splitter warps).
+// Operands that are contracted over their ROW index (weight gradients, delta propagation) are fed MN-major as they lie;
+// only operands whose row pitch is not a multiple of 16 bytes are re-laid-out by a prep kernel.
 #include "common.cuh"
 #include <cuda.h>
 #include <stdlib.h>

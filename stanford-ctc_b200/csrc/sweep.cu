@@ -7,7 +7,9 @@
 //             (brnnet.py:208-224: mvdot_col_slice on W.T + mult_slice)
 // with a batch of utterances as the second matrix dimension.
 //
-// Two kernels share this design point:
+// Three kernels share this design point (run_sweep below picks one):
+//   * sweep_tc.cu (layerSize >= 1024, round 2): the step as a tcgen05 tensor-core contraction spread over the device,
+//     split-K partials reduced through DSMEM, one counter barrier per step.
 //   * sweep_cluster.cu (H = 128/256/512): one thread-block cluster per (direction, 8 utterances); the
 //     hidden state is exchanged CTA-to-CTA through distributed shared memory with bulk async copies
 //     that complete on the consumer's mbarrier -- no global-memory round trip on the serial chain.

@@ -290,7 +290,6 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
     const int j4 = m0 + 4 * lane;
     // ring bookkeeping in units of k-block jobs g = (s - 1) * nkb + i (s = 1 .. T-1): stage g % STAGES, use g / STAGES
     uint32_t gW = 0;              // producer: next job whose W tiles have not been requested yet
-    uint32_t gM = 0;              // MMA issuer: next job to multiply
 
     // The 8 (16) M-tile CTAs of a (direction, split, K-slice) all need the SAME state tiles: each starts its walk over the
     // k-blocks at a different one, so that they do not ask L2 for the same lines at the same moment.
@@ -413,7 +412,6 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
                 }
                 __syncwarp();
             }
-            gM = g1;
             __syncwarp();
             // -------------------------------------------------------- partial product: tensor memory -> shared
             stc_mbar_wait(stc_smem_u32(done), (uint32_t)((s - 1) & 1), dead, a.err);
@@ -505,7 +503,6 @@ sweep_tc_kernel(const __grid_constant__ CUtensorMap tmW0, const __grid_constant_
             }
         }
     }
-    (void)gM;
     // no CTA may exit while a peer can still read its shared memory
     stc_fence_before();
     stc_cluster_sync();
