@@ -610,6 +610,42 @@ def run_ours(args, c):
         del acts, grad, ws
         torch.cuda.empty_cache()
 
+    # ---------------------------------------------------------------- layer contraction in isolation (tensor roofline)
+    roof_gemm = None
+    if rank == 0:
+        Mg, Ng, Kg = 48000, 2048, 2048          # the C4 forward layer of one GPU of the 8-GPU box: (T*B/8) x H x H
+        g = torch.Generator(device="cuda").manual_seed(5)
+        A_ = torch.randn(Mg, Kg, device="cuda", generator=g)
+        B_ = torch.randn(Ng, Kg, device="cuda", generator=g)
+        C_ = torch.empty(Mg, Ng, device="cuda")
+        wsg = torch.empty(max(lib.ctcb_gemm_workspace_bytes(Mg, Ng, Kg), 16), dtype=torch.uint8, device="cuda")
+        st_ = _ctcb.current_stream()
+
+        def gemm_():
+            _ctcb.check(lib.ctcb_gemm_f32(0, 1, Mg, Ng, Kg, 1.0, _ctcb.ptr(A_), Kg, _ctcb.ptr(B_), Kg, 0.0, _ctcb.ptr(C_), Ng,
+                                          None, 0, None, _ctcb.ptr(wsg), wsg.numel(), st_))
+        for _ in range(3):
+            gemm_()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            gemm_()
+        e1.record()
+        torch.cuda.synchronize()
+        msg = e0.elapsed_time(e1) / 10
+        tf = 2.0 * Mg * Ng * Kg / (msg * 1e-3) / 1e12
+        # fp32-faithful 3xTF32: three kind::tf32 MMAs per product, and TF32 runs at half the bf16 rate, so one fp32-equivalent
+        # FLOP occupies the tensor pipe like 6 bf16 FLOPs
+        roof_gemm = {"kernel": "gemm_tc_kernel<128,2,TS> (isolation, %d x %d x %d, the C4 layer of one of 8 GPUs)" % (Mg, Ng, Kg),
+                     "bound": "tensor", "achieved": 6.0 * tf, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": 6.0 * tf / pk["tf_burst"],
+                     "fp32_equivalent_tflops": tf, "ms": msg, "peak_source": pk["src"] + " bf16 burst (kernel timed alone)",
+                     "traffic": None,
+                     "note": "achieved = bf16-equivalent tensor work: 2MNK x 3 (hi.hi + hi.lo + lo.hi) x 2 (TF32 at half the bf16 rate); "
+                             "the useful fp32-equivalent rate is fp32_equivalent_tflops"}
+        del A_, B_, C_, wsg
+        torch.cuda.empty_cache()
+
     # ---------------------------------------------------------------- the other named configurations (sub-records)
     extra = {}
     if not args.headline_only:
@@ -695,7 +731,7 @@ def run_ours(args, c):
                     "api": "sgd.SGD.run(data_dict, alis, keys, sizes) with host arrays", "steps": e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "wall_s_timed_region": t_wall,
             "model_tflops": value * flops_per_utt(c) / 1e12,
-            "phases_ms": phases, "roofline": roof, "roofline_ctc": roof_ctc, "cpu_baseline": cpu,
+            "phases_ms": phases, "roofline": roof, "roofline_ctc": roof_ctc, "roofline_gemm": roof_gemm, "cpu_baseline": cpu,
             "configs": extra, "ctc_sweep": sweep_tab, "ragged_T": ragged,
             "strong_scaling_note": "configs.*_strong_b256 hold a FIXED global batch of 256 utterances split over n_gpus: "
                                    "speed-up at N = value(N) / value(1) of the same key; north_star's target is >= 6x at 8",
