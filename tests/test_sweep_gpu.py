@@ -41,7 +41,7 @@ def _ref_bptt(d, Wf, Wb, F, Bk, lens, maxAct):
                                      # the tensor-core kernel (sweep_tc.cu, H >= 1024): one and two utterance splits, partial
                                      # 16-utterance tiles, the C3 / C4 per-GPU batch widths, H not a power of two
                                      (1024, 128, 10), (1024, 40, 9), (1024, 3, 7), (2048, 32, 8), (2048, 256, 5),
-                                     (1536, 20, 6)])
+                                     (1536, 20, 6), (1024, 200, 5), (2048, 100, 4)])
 def test_sweep_forward_and_bptt(H, B, T, cuda):
     import _ctcb
     from _ctcb import lib, check, ptr
