@@ -72,7 +72,9 @@ def test_error_reporting():
     h = ctypes.c_void_p()
     assert _ctcb.lib.ctcb_brnn_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert _ctcb.lib.ctcb_ctc_workspace_bytes(4, 100, 600) == 0          # > 511 labels: unsupported
-    assert _ctcb.lib.ctcb_ctc_workspace_bytes(4, 100, 30) == 4 * 100 * 64 * 8   # fp64 alpha spill
+    # fp64 trellis rows [T][64] + one (even-padded) word per 16-frame tile; two planes for small batches (alpha and beta)
+    assert _ctcb.lib.ctcb_ctc_workspace_bytes(4, 100, 30) == 4 * (100 * 64 + 8) * 8 * 2
+    assert _ctcb.lib.ctcb_ctc_workspace_bytes(1000, 100, 30) == 1000 * (100 * 64 + 8) * 8
 
 
 def test_product_never_imports_the_oracle():

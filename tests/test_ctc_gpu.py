@@ -167,11 +167,13 @@ def test_best_path_matches_reference_semantics(cuda):
     assert ctc_fast.decode_best_path(np.asfortranarray(q)) == ([3, 3, 5], [2, 4, 7])
 
 
-@pytest.mark.parametrize("shape", ["warp", "pair"])
+@pytest.mark.parametrize("shape", ["warp", "pair", "ckpt"])
 def test_other_kernel_shapes_when_forced(shape, cuda):
     """Small batches take the three-phase latency kernel (recurrences on two warps, gradient on all warps); CTCB_CTC=warp
-    forces the one-warp-per-utterance kernel (the throughput shape of large batches), CTCB_CTC=pair the two-warp
-    meet-in-the-middle kernel (mid-sized batches), through the same golden / edge cases."""
+    forces the one-warp-per-utterance kernel that spills the trellis (large batches, long label sequences), CTCB_CTC=ckpt
+    the one-warp kernel that checkpoints and recomputes it on chip (large batches, up to 127 labels; longer ones fall
+    through to the spilling kernel), CTCB_CTC=pair the two-warp meet-in-the-middle kernel (mid-sized batches), through the
+    same golden / edge cases."""
     import os
     import subprocess
     import sys
@@ -185,9 +187,10 @@ def test_other_kernel_shapes_when_forced(shape, cuda):
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-500:]
 
 
-@pytest.mark.parametrize("T", [1, 3, 16, 17, 31, 32, 33, 47, 200])
+@pytest.mark.parametrize("T", [1, 3, 7, 8, 9, 16, 17, 31, 32, 33, 47, 200])
 def test_meet_in_the_middle_tile_boundaries(T, cuda):
-    """Utterance lengths around the 16-frame tile size: 1 tile (no first half), odd/even tile counts."""
+    """Utterance lengths around the tile sizes (16 frames; 8 in the checkpoint kernel): 1 tile (no first half), odd/even
+    tile counts."""
     rng = np.random.RandomState(100 + T)
     K = 20
     nlab = max(1, min(T // 2, 6))
