@@ -590,23 +590,35 @@ def run_ours(args, c):
         lens = torch.full((Bc,), T, dtype=torch.int32, device="cuda")
         grad = torch.empty_like(acts)
         ws = torch.empty(lib.ctcb_ctc_workspace_bytes(Bc, T, L), dtype=torch.uint8, device="cuda")
-        for _ in range(3):
-            ctc_fast.ctc_loss_batch(acts, lens, seqs, offs, L, grad=grad, workspace=ws)
-        torch.cuda.synchronize()
-        reps = 5
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            ctc_fast.ctc_loss_batch(acts, lens, seqs, offs, L, grad=grad, workspace=ws)
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / reps
         alg = Bc * (8.0 * K * T + 4.0 * L + 4.0)             # 8KT + 4|l| + 4 bytes/utt
-        roof_ctc = {"kernel": "ctc_warp_kernel (isolation, B=%d x C1 shape, %.0f MB > L2)" % (Bc, alg / 1e6),
+
+        def time_ctc(reps=5):
+            for _ in range(3):
+                ctc_fast.ctc_loss_batch(acts, lens, seqs, offs, L, grad=grad, workspace=ws)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                ctc_fast.ctc_loss_batch(acts, lens, seqs, offs, L, grad=grad, workspace=ws)
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        ms = time_ctc()
+        c1 = (T == 200 and K == 62)
+        roof_ctc = {"kernel": "ctc_warp_kernel<1,8> (isolation, B=%d x C1 shape, %.0f MB > L2)" % (Bc, alg / 1e6),
                     "bound": "hbm", "achieved": alg / (ms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": alg / (ms * 1e-3) / 1e9 / pk["hbm"],
-                    "traffic": ncu_traffic("ctc_warp_kernel") if (T == 200 and K == 62) else None,
+                    "traffic": ncu_traffic("ctc_warp_kernel") if c1 else None,
                     "utterances_per_s": Bc / (ms * 1e-3), "ms": ms, "peak_source": pk["src"]}
+        # the same batch through the checkpoint-and-recompute kernel (CTCB_CTC=ckpt): less than half the HBM traffic, more
+        # instructions -- the kernel is bound by instruction issue, so it is the slower one and not the default
+        _ctcb.check(lib.ctcb_debug_set_ctc_kernel(4))
+        ms_ck = time_ctc()
+        _ctcb.check(lib.ctcb_debug_set_ctc_kernel(0))
+        roof_ctc["checkpoint_kernel"] = {"kernel": "ctc_ckpt_kernel<1>", "ms": ms_ck, "achieved": alg / (ms_ck * 1e-3) / 1e9,
+                                         "frac": alg / (ms_ck * 1e-3) / 1e9 / pk["hbm"],
+                                         "traffic": ncu_traffic("ctc_ckpt_kernel") if c1 else None}
         del acts, grad, ws
         torch.cuda.empty_cache()
 

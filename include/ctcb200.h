@@ -96,6 +96,13 @@ int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float alpha,
                   float *C, int64_t ldc, const float *bias, int relu, const float *mask_src,
                   void *workspace, size_t ws_bytes, void *stream);
 
+/* Diagnostic / measurement: force the CTC kernel organisation used by ctcb_ctc_loss_grad_f32 (and the BRNN step).
+ * 0 = automatic (by batch size), 1 = one warp per utterance with the trellis spilled to the workspace, 2 = two warps per
+ * utterance meeting in the middle, 3 = recurrences on two warps + frame-parallel gradient (at most 256 utterances),
+ * 4 = one warp per utterance with on-chip checkpoints (at most 127 labels).  Same as the environment variable
+ * CTCB_CTC=warp|pair|par|ckpt, which is read on first use.  Results are identical whichever is chosen. */
+int ctcb_debug_set_ctc_kernel(int shape);
+
 /* Diagnostic (CTCB_GEMM_TRACE=1): SM clock stamps of CTA (0,0,0) of the last tensor-core GEMM, HOST buffer of 64 x 8
  * uint64 = per k-block {TMA issued, tile landed, low halves written, MMA thread saw it, MMAs issued, -, -, -}. */
 int ctcb_debug_gemm_trace(unsigned long long *host_out);

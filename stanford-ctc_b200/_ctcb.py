@@ -45,6 +45,7 @@ _PROTOS = {
     "ctcb_gemm_f32": (c_int, [c_int, c_int, c_int, c_int, c_int, c_f32, c_vp, c_i64, c_vp, c_i64, c_f32, c_vp,
                               c_i64, c_vp, c_int, c_vp, c_vp, c_sz, c_vp]),
     "ctcb_debug_gemm_trace": (c_int, [c_vp]),
+    "ctcb_debug_set_ctc_kernel": (c_int, [c_int]),
     "ctcb_brnn_param_count": (c_i64, [ctypes.POINTER(BrnnConfig)]),
     "ctcb_brnn_num_tensors": (c_int, [ctypes.POINTER(BrnnConfig)]),
     "ctcb_brnn_tensor_info": (c_int, [ctypes.POINTER(BrnnConfig), c_int, ctypes.POINTER(c_i64),

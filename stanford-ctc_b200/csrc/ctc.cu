@@ -663,15 +663,17 @@ __global__ void __launch_bounds__(256, P <= 2 ? (TH == 8 ? 4 : 3) : 1) ctc_warp_
     if (lane == 0) write_loss(a, u, short_utt, fail, final_sum, S, lz);
 }
 
-// Throughput shape, round 2: ONE WARP per utterance, and the trellis never leaves the SM.  The spill of the kernel above
-// costs 2 x T x 64P doubles of HBM traffic per utterance -- twice the activations and the gradient together (ncu, C1 shape,
-// B = 8192: 2.74 GB moved for 0.81 GB of algorithmic bytes).  Here pass A runs alpha over all frames and keeps only a
-// CHECKPOINT per 16-frame tile (the scaled states entering the tile and the pending power of two; the last tile's stays in
-// registers).  Pass B walks the tiles backwards: alpha of the tile's 16 frames is recomputed from its checkpoint into
-// shared memory (bit-identical: same operations on the same values), then beta runs backwards over the tile, combining
-// each frame with its alpha row into occupancies, and the gradient rows of the tile are written.  HBM sees the activations
-// twice (less the last tile, which is still in shared memory when pass B starts), the gradient once and 64P doubles per
-// 16 frames; the price is one more alpha frame per frame, on a chain that the lean frame functions above made short.
+// Throughput shape without the spill (CTCB_CTC=ckpt): ONE WARP per utterance, and the trellis never leaves the SM.  The
+// spill of the kernel above costs 2 x T x 64P doubles of HBM traffic per utterance -- more than the activations and the
+// gradient together (ncu, C1 shape, B = 8192: 2.78 GB moved for 0.81 GB of algorithmic bytes).  Here pass A runs alpha over
+// all frames and keeps only a CHECKPOINT per 8-frame tile (the scaled states entering the tile and the pending power of
+// two; the last tile's stays in registers).  Pass B walks the tiles backwards: alpha of the tile's frames is recomputed
+// from its checkpoint into shared memory (bit-identical: same operations on the same values), then beta runs backwards
+// over the tile, combining each frame with its alpha row into occupancies, and the gradient rows of the tile are written.
+// HBM sees the activations twice (less the last tile, still in shared memory when pass B starts), the gradient once and
+// 64P doubles per 8 frames: 1.29 GB at the shape above (1.58 x algorithmic).  The price is one more alpha frame per frame
+// (519 M instead of 470 M warp instructions) and an 8 KB alpha tile per warp (26 resident warps instead of 32); the kernel
+// is bound by instruction issue and chain latency, not by HBM, so it is the slower of the two and not the default.
 constexpr int TC = 8;   // frames per tile of the checkpoint kernel: 8 KB of shared memory per warp -> 26 warps per SM
 
 template <int P>
@@ -1071,6 +1073,14 @@ static int pairs_per_lane(int max_labels) {
 
 using namespace ctcb;
 
+static int g_ctc_shape = -1;    // 0 automatic, 1 warp, 2 pair, 3 par, 4 ckpt; -1: read CTCB_CTC first
+
+extern "C" int ctcb_debug_set_ctc_kernel(int shape) {
+    if (shape < 0 || shape > 4) return set_error(CTCB_EINVAL, "ctcb_debug_set_ctc_kernel: shape %d not in 0..4", shape);
+    g_ctc_shape = shape;
+    return CTCB_OK;
+}
+
 extern "C" size_t ctcb_ctc_workspace_bytes(int B, int Tmax, int max_labels) {
     const int P = pairs_per_lane(max_labels);
     if (P == 0 || B <= 0 || Tmax <= 0) return 0;
@@ -1110,13 +1120,13 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
     a.ws = (float *)workspace; a.ws_utt = ws_doubles_per_utt(Tmax, P);
 
     cudaStream_t st = (cudaStream_t)stream;
-    // few utterances (a training step): two warps per utterance meet in the middle of the trellis, one CTA each;
-    // CTCB_CTC=warp|pair|par|ckpt forces a shape (tests)
-    static int shape_env = -1;
-    if (shape_env < 0) {
+    // which kernel: chosen from the batch below; CTCB_CTC=warp|pair|par|ckpt or ctcb_debug_set_ctc_kernel force one
+    // (tests, measurements)
+    if (g_ctc_shape < 0) {
         const char *e = getenv("CTCB_CTC");
-        shape_env = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'c' ? 4 : (e[0] == 'p' && e[1] == 'a' && e[2] == 'r' ? 3 : (e[0] == 'p' ? 2 : 0))));
+        g_ctc_shape = !e ? 0 : (e[0] == 'w' ? 1 : (e[0] == 'c' ? 4 : (e[0] == 'p' && e[1] == 'a' && e[2] == 'r' ? 3 : (e[0] == 'p' ? 2 : 0))));
     }
+    const int shape_env = g_ctc_shape;
     {   // at most one utterance per SM (a training step): recurrences on two warps, gradient on all eight
         const size_t tile_b = (size_t)TT * a.Kp * sizeof(float);
         int NW = 8;
@@ -1165,9 +1175,10 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
         CTCB_LAUNCH_CHECK();
         return CTCB_OK;
     }
-    // many utterances, short label sequences: one warp each, trellis checkpointed on chip (no spill traffic).  One warp
-    // needs an 8-frame alpha tile and two activation tiles of shared memory; the block size is the smallest that reaches
-    // the largest number of resident warps per SM (ragged batches: a finished warp frees its slot at once).
+    // CTCB_CTC=ckpt: one warp per utterance, trellis checkpointed on chip instead of spilled (1.6x instead of 3.4x the
+    // algorithmic HBM bytes, but ~10 % more instructions on a kernel that is bound by instruction issue, not by HBM:
+    // 0.77 vs 0.62 ms at B = 8192 x C1 -- so it is not the default).  One warp needs an 8-frame alpha tile and two
+    // activation tiles of shared memory; the block size is the smallest that reaches the most resident warps per SM.
     {
         const size_t per_warp = (size_t)TC * 64 * P * sizeof(double) + (size_t)2 * TC * a.Kp * sizeof(float);
         int best_wpb = 0, best_warps = 0;
@@ -1179,7 +1190,7 @@ extern "C" int ctcb_ctc_loss_grad_f32(const float *acts, int is_prob, int64_t ut
             if (nblk * w > 64) nblk = 64 / w;
             if (nblk * w > best_warps) { best_warps = nblk * w; best_wpb = w; }
         }
-        const bool ckpt = (shape_env == 4 && P <= 4) || (shape_env == 0 && P == 1);
+        const bool ckpt = (shape_env == 4 && P <= 4);
         if (ckpt && best_warps >= 8) {
             const int wpb = best_wpb;
             const size_t smem = per_warp * wpb;

@@ -180,7 +180,7 @@ def test_other_kernel_shapes_when_forced(shape, cuda):
     here = os.path.dirname(os.path.abspath(__file__))
     root = os.path.dirname(here)
     code = ("import os,sys; sys.path[:0]=[%r,%r,%r]; import pytest; "
-            "sys.exit(pytest.main(['-q','-p','no:cacheprovider','-k','golden_cases or ragged_batch or pairs_per_lane or fused_softmax or tile_boundaries', %r]))"
+            "sys.exit(pytest.main(['-q','-p','no:cacheprovider','-k','golden_cases or ragged_batch or pairs_per_lane or fused_softmax or tile_boundaries or full_size', %r]))"
             % (root, os.path.join(root, "stanford-ctc_b200"), here, os.path.abspath(__file__)))
     env = dict(os.environ, CTCB_CTC=shape)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
