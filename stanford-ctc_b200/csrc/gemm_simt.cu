@@ -22,6 +22,7 @@ struct GemmArgs {
     const float *bias; int relu; const float *mask;
     float *partial;   // split-K partials [splits][M][N] (nullptr when splits == 1)
     int k_per_split;
+    int vecc;         // C (and mask / partial) rows are 16-byte aligned: the epilogue stores float4
 };
 
 __device__ __forceinline__ float epilogue(const GemmArgs &g, float acc, int m, int n) {
@@ -30,6 +31,22 @@ __device__ __forceinline__ float epilogue(const GemmArgs &g, float acc, int m, i
     if (g.bias) v += g.bias[n];
     if (g.relu) v = fmaxf(v, 0.f);
     if (g.mask) v = (g.mask[(int64_t)m * g.ldc + n] > 0.f) ? v : 0.f;
+    return v;
+}
+
+// the same on four consecutive columns (same operations in the same order: bit-identical to the scalar form)
+__device__ __forceinline__ float4 epilogue4(const GemmArgs &g, float4 acc, int m, int n) {
+    float4 v = make_float4(g.alpha * acc.x, g.alpha * acc.y, g.alpha * acc.z, g.alpha * acc.w);
+    if (g.beta != 0.f) {
+        const float4 c = *reinterpret_cast<const float4 *>(g.C + (int64_t)m * g.ldc + n);
+        v.x += g.beta * c.x; v.y += g.beta * c.y; v.z += g.beta * c.z; v.w += g.beta * c.w;
+    }
+    if (g.bias) { v.x += g.bias[n]; v.y += g.bias[n + 1]; v.z += g.bias[n + 2]; v.w += g.bias[n + 3]; }
+    if (g.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    if (g.mask) {
+        const float4 k = *reinterpret_cast<const float4 *>(g.mask + (int64_t)m * g.ldc + n);
+        v.x = (k.x > 0.f) ? v.x : 0.f; v.y = (k.y > 0.f) ? v.y : 0.f; v.z = (k.z > 0.f) ? v.z : 0.f; v.w = (k.w > 0.f) ? v.w : 0.f;
+    }
     return v;
 }
 
@@ -182,6 +199,31 @@ __global__ void __launch_bounds__(NT) gemm_simt_kernel(GemmArgs g) {
         __syncthreads();
     }
 
+    if (g.vecc) {       // 16 consecutive lanes store 16 consecutive float4 of a row: full 128-byte lines
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int m = m0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+            if (m >= g.M) continue;
+#pragma unroll
+            for (int jh = 0; jh < 2; ++jh) {
+                const int n = n0 + jh * 64 + tx * 4;
+                const float4 a4 = make_float4(acc[i][jh * 4], acc[i][jh * 4 + 1], acc[i][jh * 4 + 2], acc[i][jh * 4 + 3]);
+                if (n + 3 < g.N) {
+                    if (g.partial) *reinterpret_cast<float4 *>(g.partial + ((int64_t)blockIdx.z * g.M + m) * g.N + n) = a4;
+                    else *reinterpret_cast<float4 *>(g.C + (int64_t)m * g.ldc + n) = epilogue4(g, a4, m, n);
+                } else {
+                    const float av[4] = {a4.x, a4.y, a4.z, a4.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        if (n + e >= g.N) continue;
+                        if (g.partial) g.partial[((int64_t)blockIdx.z * g.M + m) * g.N + n + e] = av[e];
+                        else g.C[(int64_t)m * g.ldc + n + e] = epilogue(g, av[e], m, n + e);
+                    }
+                }
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
@@ -258,6 +300,11 @@ extern "C" int ctcb_gemm_f32(int transA, int transB, int M, int N, int K, float 
     splits = K > 0 ? (K + g.k_per_split - 1) / g.k_per_split : 1;
     if (splits <= 1) { g.partial = nullptr; splits = 1; }
     const bool vec = (lda % 4 == 0) && (ldb % 4 == 0) && (((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    static int vecc_env = -1;       // CTCB_GEMM_SIMT_VECC=0: scalar epilogue stores (measurement)
+    if (vecc_env < 0) { const char *e = getenv("CTCB_GEMM_SIMT_VECC"); vecc_env = e ? atoi(e) : 1; }
+    g.vecc = vecc_env && (g.partial ? (N % 4 == 0 && ((uintptr_t)g.partial) % 16 == 0)
+                                    : (ldc % 4 == 0 && ((uintptr_t)C) % 16 == 0 &&
+                                       (!mask_src || ((uintptr_t)mask_src) % 16 == 0)));
     dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, splits);
     cudaStream_t st = (cudaStream_t)stream;
 #define GO(TA, TB)                                                                  \

@@ -583,7 +583,11 @@ bool gemm_tc_enabled() {
 }
 
 // measured on B200 (tools/gemm_check.py): below these sizes the exact FFMA kernel is as fast or faster
-bool gemm_tc_eligible(int M, int N, int K) { return gemm_tc_enabled() && M >= 64 && N >= 32 && K >= 128; }
+bool gemm_tc_eligible(int M, int N, int K) {
+    static int min_k = -1;      // CTCB_GEMM_MINK: smallest contraction length that goes to the tensor cores
+    if (min_k < 0) { const char *e = getenv("CTCB_GEMM_MINK"); min_k = e ? atoi(e) : 128; }
+    return gemm_tc_enabled() && M >= 64 && N >= 32 && K >= min_k;
+}
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
     const int64_t Kp = pad4(K);

@@ -12,6 +12,8 @@ shapes = [(6400, 512, 512, 0, 1), (6400, 62, 512, 0, 1), (6400, 512, 62, 0, 0), 
 if len(sys.argv) > 1 and sys.argv[1] == "big":      # the C3 / C4 layer contractions (forward, delta, weight gradient)
     shapes = [(25600, 1024, 1024, 0, 1), (25600, 1024, 1024, 0, 0), (1024, 1024, 25600, 1, 0),
               (48000, 2048, 2048, 0, 1), (48000, 2048, 2048, 0, 0), (2048, 2048, 48000, 1, 0), (2048, 2048, 192000, 1, 0)]
+if len(sys.argv) > 1 and sys.argv[1] == "small":    # the C2 step's contractions that stay on the exact FFMA kernel
+    shapes = [(6400, 512, 41, 0, 1), (6400, 512, 62, 0, 0), (62, 512, 6400, 1, 0), (512, 41, 6400, 1, 0)]
 if len(sys.argv) > 1 and sys.argv[1] == "quick":
     shapes = shapes[-3:] + shapes[:1]
 for (M, N, K, ta, tb) in shapes:
