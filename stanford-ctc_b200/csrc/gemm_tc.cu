@@ -582,11 +582,13 @@ bool gemm_tc_enabled() {
     return on == 1;
 }
 
-// measured on B200 (tools/gemm_check.py): below these sizes the exact FFMA kernel is as fast or faster
+// measured on B200 (tools/gemm_check.py): below these sizes the exact FFMA kernel is as fast or faster (K = 41 / 62 with
+// re-pitched copies: slower on the tensor cores; M = 62, K = 6400 -- the output layer's weight gradient: 44 -> 24 us on them)
 bool gemm_tc_eligible(int M, int N, int K) {
-    static int min_k = -1;      // CTCB_GEMM_MINK: smallest contraction length that goes to the tensor cores
+    static int min_k = -1, min_m = -1;      // CTCB_GEMM_MINK / _MINM: smallest contraction length / row count that goes to the tensor cores
     if (min_k < 0) { const char *e = getenv("CTCB_GEMM_MINK"); min_k = e ? atoi(e) : 128; }
-    return gemm_tc_enabled() && M >= 64 && N >= 32 && K >= min_k;
+    if (min_m < 0) { const char *e = getenv("CTCB_GEMM_MINM"); min_m = e ? atoi(e) : 32; }
+    return gemm_tc_enabled() && M >= min_m && N >= 32 && K >= min_k;
 }
 
 size_t gemm_tc_workspace_bytes(int M, int N, int K) {
