@@ -7,16 +7,27 @@
 // grad = p - occupancy/(p*absum) (:139-145), skip when a normaliser is 0 (:147-149) -- but laid
 // out for the GPU:
 //
-//   * one WARP per utterance.  Trellis states are held in registers: lane owns P consecutive
-//     (blank,label) pairs, s = 2i and 2i+1; the s-1/s-2 neighbours of the recurrence come from one
-//     __shfl_up (alpha) / two __shfl_down (beta) per frame, the frame normaliser from a
-//     warp-shuffle butterfly.  No block barrier anywhere.
-//   * the T x K activations are streamed in TIME TILES of TT frames: a coalesced copy into shared
-//     memory, then the softmax statistics of all TT frames at once (2 lanes per frame, off the
-//     serial chain); the recurrence then gathers p[label] from the shared-memory tile.
-//   * alpha-tilde is spilled to a [T][2*32*P] fp64 workspace (coalesced double2 per pair) and read
-//     back, prefetched, by the beta sweep, which scatters the normalised occupancies into a
-//     shared-memory tile; the gradient of a whole tile is then written with coalesced row stores.
+//   * Trellis states are held in registers: a lane owns P consecutive (blank,label) pairs, s = 2i and
+//     2i+1; the s-1/s-2 neighbours of the recurrence come from one __shfl_up (alpha) / two
+//     __shfl_down (beta) per frame, the per-frame rescaling from an integer REDUX.MAX over the
+//     exponents (a power of two, applied one frame later).  No block barrier on the serial chain.
+//   * the T x K activations are streamed in TIME TILES of 16 (or 8) frames: a coalesced copy into
+//     shared memory, then the softmax statistics of all frames of the tile at once (2 or 4 lanes
+//     per frame, off the serial chain); the recurrence then gathers e[label] from the tile.
+//   * occupancies are scattered into a shared-memory tile as 2^30 fixed point (integer atomics:
+//     order-independent, bit-reproducible); the gradient of a whole tile is then written with
+//     coalesced row stores.
+//
+// Four kernel organisations over the same frame functions (chosen by batch size in
+// ctcb_ctc_loss_grad_f32; CTCB_CTC / ctcb_debug_set_ctc_kernel force one; results are identical):
+//   ctc_par_kernel   at most one utterance per SM (a training step): alpha on warp 0 and beta on warp 1
+//                    over all frames at the same time, both spilled; then all warps turn the two planes
+//                    into occupancies and gradient, one time tile each.
+//   ctc_pair_kernel  a few utterances per SM: two warps meet in the middle of the trellis.
+//   ctc_warp_kernel  large batches: one warp per utterance, alpha-tilde spilled to a [T][64P] fp64
+//                    workspace (coalesced double2 per pair), read back by the beta sweep.
+//   ctc_ckpt_kernel  the same without the spill: alpha checkpointed every 8 frames and recomputed per
+//                    tile in shared memory (less than half the HBM traffic, more instructions; slower).
 //
 // Scaling is arbitrary per frame (the gradient divides by absum[t], ctc_fast.pyx:133-145), so the
 // recurrences run on e = exp(x - max) and the log-partition is added to the loss separately.
@@ -627,7 +638,7 @@ __global__ void __launch_bounds__(256, P <= 2 ? (TH == 8 ? 4 : 3) : 1) ctc_warp_
 
     const bool short_utt = (c.T < q.nlab);
     bool fail = (c.T <= 0);
-    float logZ = 0.f;     // lanes < TT accumulate log Z of the rows they own
+    float logZ = 0.f;     // lanes < TH accumulate log Z of the rows they own
     int S = 0;            // accumulated power-of-two scaling of alpha
     double final_sum = 1.0;
 
