@@ -72,6 +72,9 @@ def test_error_reporting():
     h = ctypes.c_void_p()
     assert _ctcb.lib.ctcb_brnn_create(ctypes.byref(bad), ctypes.byref(h)) == -1
     assert _ctcb.lib.ctcb_ctc_workspace_bytes(4, 100, 600) == 0          # > 511 labels: unsupported
+    # the CTC kernel selector takes 0..4 (automatic, warp, pair, par, ckpt) and nothing else
+    assert _ctcb.lib.ctcb_debug_set_ctc_kernel(7) == -1 and b"not in 0..4" in _ctcb.lib.ctcb_last_error()
+    assert _ctcb.lib.ctcb_debug_set_ctc_kernel(0) == 0
     # fp64 trellis rows [T][64] + one (even-padded) word per 16-frame tile; two planes for small batches (alpha and beta)
     assert _ctcb.lib.ctcb_ctc_workspace_bytes(4, 100, 30) == 4 * (100 * 64 + 8) * 8 * 2
     assert _ctcb.lib.ctcb_ctc_workspace_bytes(1000, 100, 30) == 1000 * (100 * 64 + 8) * 8
